@@ -1,0 +1,289 @@
+"""Benchmark of the KS hot path on B200:  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): a batch of 4096 random OrbitKS 32x32 seeds (reference generator,
+T=44, L=33.4).  One "step" = one fused residual+adjoint evaluation (cost = 1/2|F|^2 and grad = J^T F incl. the
+parameter components) of every orbit in the batch = 4096 evals.  `value` = evals/s with inputs resident in HBM;
+`e2e` = the same through the public BatchedOrbitKS API from pinned HOST buffers (H2D of modes+params and D2H of
+cost+gradient inside the timed region).  The timed loop rotates over several distinct input/output sets so the
+working set exceeds the 126 MB L2.  Under torchrun every rank evaluates its own 4096 seeds (weak scaling, no
+collective on the data path; one all_reduce(MAX) of the elapsed time and one gather of per-rank results).
+
+`--impl reference` times the CPU arm instead: the NumPy oracle port of the reference's path (the reference itself is
+Python and /root/reference does not exist on the GPU box) on all host cores, same workload / metric / unit.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GRID, M_GRID, BATCH = 32, 32, 4096
+T0, L0 = 44.0, 33.4
+NM = (N_GRID - 1) * (M_GRID - 2)
+ALG_BYTES_PER_EVAL = 8 * (2 * NM + 7)  # read modes+params, write grad modes+params+cost
+METRIC = "orbit residual+adjoint evals/sec (OrbitKS 32x32)"
+UNIT = "evals/s"
+
+
+def make_seeds(first, count):
+    """Reference-generator seeds (ks/orbits.py:1738) through the product's own populate()."""
+    from orbithunter_b200 import OrbitKS
+
+    out = np.empty((count, N_GRID - 1, M_GRID - 2))
+    for i in range(count):
+        out[i] = OrbitKS(parameters=(T0, L0, 0.0)).populate(attr="state", seed=first + i, discretization=(N_GRID, M_GRID)).state
+    return out
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, val in zip(names, f[2:]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_port_evals_per_s(modes, params, budget_s, procs):
+    """Oracle port (NumPy restatement of the reference path), one process per core, for about budget_s seconds."""
+    import multiprocessing as mp
+
+    if procs == 1:  # in-process: never fork a process that holds a CUDA context
+        t0 = time.perf_counter()
+        n_done = _cpu_worker(modes, params, budget_s)
+        return n_done / (time.perf_counter() - t0), n_done
+    chunks = np.array_split(np.arange(modes.shape[0]), procs)
+    with mp.get_context("fork").Pool(procs) as pool:
+        t0 = time.perf_counter()
+        reps = pool.starmap(_cpu_worker, [(modes[c], params[c], budget_s) for c in chunks if len(c)])
+        dt = time.perf_counter() - t0
+    return sum(reps) / dt, sum(reps)
+
+
+def _cpu_worker(modes, params, budget_s):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import ks_oracle as ko
+
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        ko.costgrad(modes, params, ko.ORBIT)
+        done += modes.shape[0]
+    return done
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 64 * cores
+    modes = make_seeds_cpu(sample)
+    params = np.tile([T0, L0, 0.0], (sample, 1))
+    per_step_budget = max(1.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    for _ in range(args.warmup):
+        cpu_port_evals_per_s(modes, params, min(per_step_budget, 2.0), cores)
+    rates, t_all = [], time.perf_counter()
+    for _ in range(args.steps):
+        r, _n = cpu_port_evals_per_s(modes, params, per_step_budget, cores)
+        rates.append(r)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"batch of {BATCH} random OrbitKS 32x32 seeds, residual+adjoint evaluation", "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} seeds, batched NumPy oracle, one process per core, {per_step_budget:.1f} s per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+
+
+def make_seeds_cpu(count):
+    from oracle import ks_oracle as ko
+
+    return np.stack([ko.populate_state(T0, L0, N_GRID, M_GRID, s, ko.ORBIT) for s in range(count)])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--sets", type=int, default=4, help="distinct input/output sets rotated to exceed L2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from orbithunter_b200 import BatchedOrbitKS, _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    # ---- inputs: this rank's 4096 seeds, replicated into `sets` perturbed copies (distinct memory, same statistics) ----
+    base = make_seeds(rank * BATCH, BATCH)
+    params_h = np.tile([T0, L0, 0.0], (BATCH, 1))
+    sets = []
+    for s in range(args.sets):
+        orb = BatchedOrbitKS(torch.as_tensor(base * (1.0 + 1e-3 * s)), torch.as_tensor(params_h), "OrbitKS", "modes")
+        sets.append({"orb": orb, "cost": torch.empty(BATCH, dtype=torch.float64, device=dev),
+                     "g": torch.empty_like(orb.state), "gp": torch.empty_like(orb.parameters)})
+    ws_bytes = L.ks_workspace_bytes(0, N_GRID, M_GRID, BATCH)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i):
+        s = sets[i % len(sets)]
+        o = s["orb"]
+        _lib.check(L.ks_costgrad(0, N_GRID, M_GRID, BATCH, o.state.data_ptr(), o.parameters.data_ptr(), o.cmask, 0,
+                                 s["cost"].data_ptr(), s["g"].data_ptr(), s["gp"].data_ptr(), None, ws.data_ptr(), ws_bytes, stream))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for i in range(args.steps):
+            step(i)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        # ---- end-to-end through the public API from pinned host buffers ----
+        hm = torch.as_tensor(base).pin_memory()
+        hp = torch.as_tensor(params_h).pin_memory()
+        hg = torch.empty((BATCH, N_GRID - 1, M_GRID - 2), dtype=torch.float64).pin_memory()
+        hgp = torch.empty((BATCH, 3), dtype=torch.float64).pin_memory()
+        hc = torch.empty(BATCH, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            orb = BatchedOrbitKS(hm.to(dev, non_blocking=True), hp.to(dev, non_blocking=True), "OrbitKS", "modes")
+            cost, grad = orb.costgrad()
+            hg.copy_(grad.state, non_blocking=True)
+            hgp.copy_(grad.parameters, non_blocking=True)
+            hc.copy_(cost, non_blocking=True)
+
+        e2e_steps = max(3, min(args.steps, 50))
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    checksum = float(sets[0]["cost"].sum().item())
+    if world > 1:  # the only data-path collective: final result gather (40 B/orbit in the real sweep)
+        res = torch.stack([sets[0]["cost"].sum(), sets[0]["gp"].abs().sum()])
+        gathered = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
+        dist.gather(res, gathered, dst=0)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = ms / args.steps
+    value = world * BATCH / (ms_per_step * 1e-3)
+    e2e_value = world * BATCH / (e2e_ms / e2e_steps * 1e-3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = BATCH * ALG_BYTES_PER_EVAL / (ms_per_step * 1e-3) / 1e9  # per GPU: one launch = 4096 evals
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("costgrad_32x32_bytes_per_launch")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"batch of {BATCH} random OrbitKS 32x32 seeds per GPU (T=44, L=33.4, reference generator), "
+                               "fused residual+adjoint (cost + J^T F) evaluation; BASELINE configs[1] shape",
+                   "batch_per_gpu": BATCH, "grid": [N_GRID, M_GRID], "class": "OrbitKS",
+                   "l2": f"rotating {len(sets)} input/output sets ({len(sets) * BATCH * ALG_BYTES_PER_EVAL / 1e6:.0f} MB) > 126 MB L2",
+                   "parallelism": f"orbits sharded over {world} GPU(s), no data-path collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "ks_warp32_kernel<OrbitKS,COSTGRAD>",
+                     "algorithmic_bytes_per_launch": BATCH * ALG_BYTES_PER_EVAL,
+                     "note": "fp64-pipe bound by design (SURVEY 7/8d): ~3.7k fp64 instr per warp-eval of 2 orbits"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * (NM + 3) * 8,
+                "d2h_bytes_per_step": BATCH * (NM + 3 + 1) * 8, "steps": e2e_steps},
+        "gpu_launches": args.steps, "clocks": clocks.summary(), "checksum_cost_sum": checksum,
+    }
+    if not args.no_cpu_baseline:
+        cores = 1
+        sample = 256
+        cm = make_seeds_cpu(sample)
+        rate, n_done = cpu_port_evals_per_s(cm, np.tile([T0, L0, 0.0], (sample, 1)), 10.0, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{sample} seeds of the same workload, batched NumPy oracle on one core for 10 s ({n_done} evals)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,77 @@
+/* ks_b200.h -- C ABI of the B200-native Kuramoto-Sivashinsky orbit engine (libks_b200.so).
+ *
+ * Drop-in boundary for the spatiotemporal KS hot path of chaotic-systems/orbithunter.  The reference is pure
+ * Python and has NO FFI; its boundary is the Orbit-subclass method protocol (template/class_template.py:277-461).
+ * Each entry point below is the batched device implementation of one of those methods; the Python mirror in
+ * orbithunter_b200/ (same class / method / kwarg names as the reference) binds them with ctypes.  INTEGRATION.md
+ * shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - all array arguments are DEVICE pointers to C-contiguous float64 with a leading batch axis;
+ *   - `modes[B][rows][cols]`: the reference's real-packed spatiotemporal Fourier modes; rows = n-1,
+ *     cols = m-2 (OrbitKS, RelativeOrbitKS) or m/2-1 (ShiftReflectionOrbitKS, AntisymmetricOrbitKS)
+ *     (orbithunter/ks/orbits.py:1403-1412, :3677-3686, :3254-3263);
+ *   - `params[B][3]` = (T, L, S) = parameter labels ("t","x","s") (ks/orbits.py:207-221);
+ *   - `cmask`: bit0/1/2 set = t/x/s held constant (the reference's `constraints` dict, core.py:1617-1664);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls only enqueue work;
+ *   - `ws`/`ws_bytes`: caller-owned scratch of at least ks_workspace_bytes(...) bytes (may be NULL when that is 0);
+ *   - return value 0 = enqueued; negative = argument / launch error (message via ks_last_error()); never throws.
+ * No entry point allocates device memory or has a CPU fallback.
+ */
+#ifndef KS_B200_H
+#define KS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { KS_CLS_ORBIT = 0, KS_CLS_RELATIVE = 1, KS_CLS_SHIFT_REFLECTION = 2, KS_CLS_ANTISYMMETRIC = 3 };
+enum { KS_BASIS_FIELD = 0, KS_BASIS_SPATIAL_MODES = 1, KS_BASIS_MODES = 2 };
+enum { KS_ERR_ARG = -1, KS_ERR_SHAPE = -2, KS_ERR_WORKSPACE = -3, KS_ERR_LAUNCH = -4 };
+
+int ks_b200_abi_version(void);
+const char* ks_last_error(void);
+
+/* test hook: route 32x32 through the generic-size kernel instead of the register-resident one (cross-check). */
+void ks_debug_force_generic(int on);
+
+/* rows*cols of the modes basis for (cls, n, m); 0 if the shape is not supported. */
+int ks_mode_size(int cls, int n, int m);
+/* scratch bytes required by any of the calls below for this shape and batch. */
+size_t ks_workspace_bytes(int cls, int n, int m, int batch);
+
+/* OrbitKS.transform (ks/orbits.py:231-303) and the class-specific overrides: any basis -> any basis. */
+int ks_transform(int cls, int n, int m, int batch, int from_basis, int to_basis, const double* in, double* out,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* OrbitKS.eqn (ks/orbits.py:526-555) + Orbit.cost (core.py:986-1008): F(u) and 1/2 |F|^2 (cost may be NULL). */
+int ks_eqn(int cls, int n, int m, int batch, const double* modes, const double* params, double* f_out,
+           double* cost_out, void* ws, size_t ws_bytes, void* stream);
+
+/* OrbitKS.matvec (ks/orbits.py:659-709; Relative :2623-2660): J(u) v, with vparams = (dT, dL, dS). */
+int ks_matvec(int cls, int n, int m, int batch, const double* modes, const double* params, const double* vmodes,
+              const double* vparams, uint32_t cmask, double* out_state, void* ws, size_t ws_bytes, void* stream);
+
+/* OrbitKS.rmatvec (ks/orbits.py:711-755, :1984-2045; Relative :3059-3115): J(u)^T v -> state + 3 parameters. */
+int ks_rmatvec(int cls, int n, int m, int batch, const double* modes, const double* params, const double* vmodes,
+               uint32_t cmask, double* out_state, double* out_params, void* ws, size_t ws_bytes, void* stream);
+
+/* eqn followed by OrbitKS.costgrad (ks/orbits.py:757-791), fused: cost = 1/2|F|^2, grad = J^T F, optionally
+ * rescaled by OrbitKS.precondition (:1034-1089).  f_out may be NULL. */
+int ks_costgrad(int cls, int n, int m, int batch, const double* modes, const double* params, uint32_t cmask,
+                int preconditioning, double* cost_out, double* grad_state, double* grad_params, double* f_out,
+                void* ws, size_t ws_bytes, void* stream);
+
+/* OrbitKS.precondition (ks/orbits.py:1034-1089): state / (|w_j| + q^2 + q^4); unconstrained t *= T^-pexp_t,
+ * x *= L^-pexp_x (reference default pexp = (1, 4)); `params` supplies (T, L) (the reference's `pmult`).
+ * gparams_in/out may both be NULL. */
+int ks_precondition(int cls, int n, int m, int batch, const double* state_in, const double* gparams_in,
+                    const double* params, uint32_t cmask, double pexp_t, double pexp_x, double* state_out,
+                    double* gparams_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KS_B200_H */

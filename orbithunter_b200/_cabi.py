@@ -1,0 +1,30 @@
+"""ctypes signatures of the C ABI declared in include/ks_b200.h (one place, used by the loader and by the tests)."""
+import ctypes as C
+
+_P = C.c_void_p
+_SIG = {
+    "ks_b200_abi_version": (C.c_int, []),
+    "ks_last_error": (C.c_char_p, []),
+    "ks_debug_force_generic": (None, [C.c_int]),
+    "ks_mode_size": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "ks_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ks_transform": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "ks_eqn": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "ks_matvec": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_uint32, _P, _P, C.c_size_t, _P]),
+    "ks_rmatvec": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_uint32, _P, _P, _P, C.c_size_t, _P]),
+    "ks_costgrad": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_uint32, C.c_int, _P, _P, _P, _P, _P,
+                              C.c_size_t, _P]),
+    "ks_precondition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_uint32, C.c_double, C.c_double, _P, _P,
+                                  _P]),
+}
+
+EXPORTS = tuple(_SIG)
+
+
+def bind(lib):
+    """Attach restype/argtypes for every exported symbol; raises AttributeError if one is missing."""
+    for name, (res, args) in _SIG.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib

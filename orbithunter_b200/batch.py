@@ -1,0 +1,243 @@
+"""Batched orbit container: B independent KS orbits of one class and discretization, resident on one GPU.
+
+Mirrors, with a leading batch axis, the part of the reference's ``Orbit``/``OrbitKS`` protocol that the solver
+drivers touch (reference orbithunter/core.py: cost :986, dot :864, cdof :1617, constants :1645, increment :1760;
+orbithunter/ks/orbits.py: transform :231, eqn :526, matvec :659, rmatvec :711, costgrad :757, precondition :1034,
+from_numpy_array :305).  PyTorch owns the device memory; every numerical method is one call into libks_b200.so.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CLASS_IDS = {"OrbitKS": 0, "RelativeOrbitKS": 1, "ShiftReflectionOrbitKS": 2, "AntisymmetricOrbitKS": 3}
+CLASS_NAMES = {v: k for k, v in CLASS_IDS.items()}
+BASIS_IDS = {"field": 0, "spatial_modes": 1, "modes": 2}
+PARAMETER_LABELS = ("t", "x", "s")
+
+
+def default_constraints(cls_id):
+    """ks/orbits.py:1731-1736; RelativeOrbitKS :3035-3036."""
+    return {"t": False, "x": False, "s": cls_id != 1}
+
+
+def constraint_mask(constraints):
+    return sum(1 << i for i, lab in enumerate(PARAMETER_LABELS) if constraints.get(lab, True))
+
+
+def basis_shape(cls_id, n, m, basis):
+    """ks/orbits.py:1403-1412, :3254-3263, :3677-3686."""
+    if basis == "field":
+        return n, m
+    if basis == "spatial_modes":
+        return n, m - 2
+    return (n - 1, m - 2) if cls_id in (0, 1) else (n - 1, m // 2 - 1)
+
+
+_WORKSPACES = {}
+
+
+def workspace(device, nbytes):
+    """Per-device scratch buffer, grown on demand (sized by ks_workspace_bytes); never shrinks."""
+    key = torch.device(device).index or 0
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class BatchedOrbitKS:
+    """B orbits: ``state`` (B, rows, cols) float64 CUDA tensor in ``basis``; ``parameters`` (B, 3) = (T, L, S)."""
+
+    def __init__(self, state, parameters, cls="OrbitKS", basis="modes", discretization=None, constraints=None):
+        self.cls_id = CLASS_IDS[cls] if isinstance(cls, str) else int(cls)
+        if not torch.is_tensor(state):
+            state = torch.as_tensor(np.ascontiguousarray(state, dtype=np.float64))
+        if not torch.is_tensor(parameters):
+            parameters = torch.as_tensor(np.ascontiguousarray(parameters, dtype=np.float64))
+        if state.dim() != 3:
+            raise ValueError('"state" must have shape (batch, rows, cols)')
+        if basis not in BASIS_IDS:
+            raise ValueError('basis not recognized; must equal "field" or "spatial_modes", or "modes"')
+        if not state.is_cuda:
+            if not torch.cuda.is_available():
+                raise _lib.KsB200Error("orbithunter_b200 needs a CUDA device; there is no CPU path")
+            state = state.cuda()
+        self.state = state.to(torch.float64).contiguous()
+        self.parameters = parameters.to(self.state.device, torch.float64).reshape(-1, 3).contiguous()
+        if self.parameters.shape[0] != self.state.shape[0]:
+            raise ValueError("parameters must have shape (batch, 3)")
+        self.basis = basis
+        if discretization is None:
+            r, c = self.state.shape[1:]
+            if basis == "field":
+                discretization = (r, c)
+            elif basis == "spatial_modes":
+                discretization = (r, c + 2)
+            else:
+                discretization = (r + 1, c + 2) if self.cls_id in (0, 1) else (r + 1, 2 * c + 2)
+        self.discretization = tuple(int(x) for x in discretization)
+        if tuple(self.state.shape[1:]) != basis_shape(self.cls_id, *self.discretization, basis):
+            raise ValueError(f"state shape {tuple(self.state.shape[1:])} inconsistent with {self.discretization} in {basis}")
+        cons = default_constraints(self.cls_id)
+        if constraints:
+            cons.update(constraints)
+        self.constraints = cons
+
+    # ---- bookkeeping -------------------------------------------------------------------------------------------
+    @property
+    def n(self):
+        return self.discretization[0]
+
+    @property
+    def m(self):
+        return self.discretization[1]
+
+    @property
+    def batch(self):
+        return self.state.shape[0]
+
+    @property
+    def cmask(self):
+        return constraint_mask(self.constraints)
+
+    @property
+    def cls_name(self):
+        return CLASS_NAMES[self.cls_id]
+
+    def __len__(self):
+        return self.batch
+
+    def _like(self, state=None, parameters=None, basis=None):
+        return BatchedOrbitKS(self.state if state is None else state, self.parameters if parameters is None else parameters,
+                              self.cls_id, self.basis if basis is None else basis, self.discretization, self.constraints)
+
+    def copy(self):
+        return self._like(self.state.clone(), self.parameters.clone())
+
+    def _call(self, fn, *args):
+        L = _lib.lib()
+        nbytes = L.ks_workspace_bytes(self.cls_id, self.n, self.m, self.batch)
+        ws = workspace(self.state.device, nbytes)
+        with torch.cuda.device(self.state.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(getattr(L, fn)(self.cls_id, self.n, self.m, self.batch, *args, ws.data_ptr(), ws.numel(), stream))
+
+    def _need_modes(self):
+        assert self.basis == "modes", "Convert to spatiotemporal Fourier mode basis first (reference ks/orbits.py:541)"
+
+    # ---- reference protocol, batched ---------------------------------------------------------------------------
+    def transform(self, to=None):
+        if to not in BASIS_IDS:
+            raise ValueError("Trying to transform to unrecognized basis.")
+        if to == self.basis:
+            return self
+        out = torch.empty((self.batch,) + basis_shape(self.cls_id, self.n, self.m, to), dtype=torch.float64,
+                          device=self.state.device)
+        self._call("ks_transform", BASIS_IDS[self.basis], BASIS_IDS[to], _ptr(self.state), _ptr(out))
+        return self._like(out, basis=to)
+
+    def eqn(self, return_cost=False):
+        self._need_modes()
+        F = torch.empty_like(self.state)
+        cost = torch.empty(self.batch, dtype=torch.float64, device=self.state.device)
+        self._call("ks_eqn", _ptr(self.state), _ptr(self.parameters), _ptr(F), _ptr(cost))
+        out = self._like(F)
+        return (out, cost) if return_cost else out
+
+    def cost(self, evaleqn=True):
+        if evaleqn:
+            return self.eqn(return_cost=True)[1]
+        v = self.state.reshape(self.batch, -1)
+        return 0.5 * (v * v).sum(dim=1)
+
+    def matvec(self, other):
+        self._need_modes()
+        out = torch.empty_like(self.state)
+        self._call("ks_matvec", _ptr(self.state), _ptr(self.parameters), _ptr(other.state), _ptr(other.parameters), self.cmask,
+                   _ptr(out))
+        return self._like(out)
+
+    def rmatvec(self, other):
+        self._need_modes()
+        out = torch.empty_like(self.state)
+        op = torch.empty_like(self.parameters)
+        self._call("ks_rmatvec", _ptr(self.state), _ptr(self.parameters), _ptr(other.state), self.cmask, _ptr(out), _ptr(op))
+        return self._like(out, op)
+
+    def costgrad(self, preconditioning=False, return_eqn=False):
+        """(cost, gradient orbit[, F orbit]): eqn + costgrad of the reference fused into one launch."""
+        self._need_modes()
+        g = torch.empty_like(self.state)
+        gp = torch.empty_like(self.parameters)
+        cost = torch.empty(self.batch, dtype=torch.float64, device=self.state.device)
+        F = torch.empty_like(self.state) if return_eqn else None
+        self._call("ks_costgrad", _ptr(self.state), _ptr(self.parameters), self.cmask, int(bool(preconditioning)), _ptr(cost),
+                   _ptr(g), _ptr(gp), _ptr(F))
+        grad = self._like(g, gp)
+        return (cost, grad, self._like(F)) if return_eqn else (cost, grad)
+
+    def precondition(self, pmult=None, pexp=(1, 4)):
+        """ks/orbits.py:1034-1089: rescale this (gradient / correction) orbit with respect to ``pmult``'s (T, L)."""
+        ref = self.parameters if pmult is None else pmult
+        out = torch.empty_like(self.state)
+        gp = torch.empty_like(self.parameters)
+        L = _lib.lib()
+        with torch.cuda.device(self.state.device):
+            _lib.check(L.ks_precondition(self.cls_id, self.n, self.m, self.batch, _ptr(self.state), _ptr(self.parameters),
+                                         _ptr(ref.contiguous()), self.cmask, float(pexp[0]), float(pexp[1]), _ptr(out), _ptr(gp),
+                                         torch.cuda.current_stream().cuda_stream))
+        return self._like(out, gp)
+
+    def dot(self, other):
+        return (self.state.reshape(self.batch, -1) * other.state.reshape(self.batch, -1)).sum(dim=1)
+
+    def norm(self):
+        return torch.linalg.vector_norm(self.state.reshape(self.batch, -1), dim=1)
+
+    def increment(self, other, step_size=1.0):
+        """core.py:1760-1796; ``step_size`` may be a scalar or a (B,) tensor."""
+        if torch.is_tensor(step_size):
+            s3, s2 = step_size.reshape(-1, 1, 1), step_size.reshape(-1, 1)
+        else:
+            s3 = s2 = step_size
+        return self._like(self.state + s3 * other.state, self.parameters + s2 * other.parameters)
+
+    def free_indices(self):
+        return [i for i, lab in enumerate(PARAMETER_LABELS) if not self.constraints.get(lab, True)]
+
+    def cdof(self):
+        """[state.ravel(), free parameters] per orbit; core.py:1617-1643."""
+        return torch.cat((self.state.reshape(self.batch, -1), self.parameters[:, self.free_indices()]), dim=1)
+
+    def from_cdof(self, vec, constants=None):
+        """Inverse of cdof; constrained parameters from ``constants`` (B,3) or 0 (ks/orbits.py:343-377)."""
+        size = self.state.shape[1] * self.state.shape[2]
+        params = torch.zeros_like(self.parameters) if constants is None else constants.clone()
+        if constants is not None:
+            params[:, self.free_indices()] = 0.0
+        for slot, i in enumerate(self.free_indices()):
+            params[:, i] = vec[:, size + slot]
+        return self._like(vec[:, :size].reshape(self.state.shape).contiguous(), params)
+
+    # ---- host <-> device ---------------------------------------------------------------------------------------
+    def cpu_state(self):
+        return self.state.cpu().numpy()
+
+    def cpu_parameters(self):
+        return self.parameters.cpu().numpy()
+
+    def __getitem__(self, i):
+        """Single-orbit view as a drop-in OrbitKS-family instance (host arrays)."""
+        from .ks import CLASSES
+
+        p = tuple(float(x) for x in self.parameters[i].cpu().numpy())
+        return CLASSES[self.cls_name](state=self.state[i].cpu().numpy(), basis=self.basis, parameters=p,
+                                      discretization=self.discretization, constraints=dict(self.constraints))

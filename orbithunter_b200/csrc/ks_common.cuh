@@ -1,0 +1,40 @@
+// Shared definitions for the KS hot-path kernels (class ids, op ids, argument block, small helpers).
+#pragma once
+#include <utility>
+
+#include "ks_platform.cuh"
+
+// class ids: the four symmetry classes named by the north star (reference orbithunter/ks/orbits.py:24, :2554,
+// :3582, :3189).  Numbering is shared with include/ks_b200.h and oracle/ks_oracle.py.
+enum { KS_ORBIT = 0, KS_RELATIVE = 1, KS_SHIFT_REFLECTION = 2, KS_ANTISYMMETRIC = 3 };
+// fused evaluation ops
+enum { KS_OP_EQN = 0, KS_OP_COSTGRAD = 1, KS_OP_MATVEC = 2, KS_OP_RMATVEC = 3 };
+// constraint mask bits (set = parameter held constant; reference core.py:1617-1664 `constraints`)
+enum { KS_FIX_T = 1, KS_FIX_X = 2, KS_FIX_S = 4 };
+
+struct KsEvalArgs {
+  const double* modes;    // [B, Nm]   u in the modes basis
+  const double* params;   // [B, 3]    (T, L, S)
+  const double* vmodes;   // [B, Nm]   v (matvec / rmatvec), else null
+  const double* vparams;  // [B, 3]    (dT, dL, dS) increments (matvec), else null
+  double* out_state;      // [B, Nm]   F (eqn) | grad (costgrad) | J v | J^T v
+  double* out_params;     // [B, 3]    parameter components of grad / J^T v (0 where constrained), or null
+  double* out_cost;       // [B]       1/2 |F|^2 (eqn, costgrad), or null
+  double* f_out;          // [B, Nm]   costgrad only: also emit F; null -> per-warp scratch is used instead
+  double* scratch;        // workspace (ks_workspace_bytes)
+  int batch;
+  unsigned cmask;
+  int precond;            // costgrad: apply the reference's diagonal preconditioner (ks/orbits.py:1034-1089)
+};
+
+namespace ks {
+template <int B, int E, class F>
+KS_DEVI void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+constexpr double kSqrt2 = 1.4142135623730950488016887242097;
+}  // namespace ks

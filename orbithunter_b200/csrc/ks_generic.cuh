@@ -1,0 +1,526 @@
+// Generic-size fused spectral kernels: one CTA per orbit, any even n, m >= 4 (power of two or not).
+//
+// Same mathematics and tuple algebra as ks_warp32.cuh (see the layout notes there), but the 1-D transforms are done
+// by a warp cooperatively on a line held in shared memory (radix-2 for powers of two, direct O(N^2) DFT otherwise,
+// which covers the reference fixtures' 26- and 34-point grids), and the intermediate arrays (complex spatial modes
+// XC[k][n], field FU[n][m], stage-1 state TU[Nm]) live in a per-CTA slot of the caller's workspace, i.e. in L2.
+// This is the path for 64x64 ... 256x256 and for the transform API; it is the correctness baseline that the
+// size-specialised kernels are checked against and is not yet tuned (multi-pass through L2, strided transposes).
+//
+// Reference path replaced: orbithunter/ks/orbits.py transforms :2212-2420, :3472-3579, :3869-4005; eqn :526-555;
+// matvec :659-709, :2623-2660; rmatvec :711-755, :1984-2045, :3059-3115; costgrad :757-791; precondition :1034-1089.
+#pragma once
+#include "ks_common.cuh"
+#include "ks_warp32.cuh"  // Tup algebra
+
+namespace ksg {
+using ksw32::Tup;
+using ksw32::dot_tup;
+using ksw32::dx_tup;
+using ksw32::rot_t;
+using ksw32::rot_x;
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+enum { KS_OP_TRANSFORM = 4 };
+
+struct Geom {
+  int n, m, h, k, cols, nm, nmax;
+  int log_n, log_m;  // -1 when not a power of two
+  double ct, cx;     // 1/sqrt(2n), 1/sqrt(2m)
+};
+struct GenArgs {
+  KsEvalArgs e;
+  Geom g;
+  int from_basis, to_basis;  // transform op
+  const double* tin;
+  double* tout;
+  size_t slot_doubles;  // workspace doubles per CTA slot
+};
+
+KS_HD size_t slot_doubles(int n, int m, int cols) {
+  const size_t k = m / 2 - 1;
+  return 2 * k * n + (size_t)n * m + (size_t)(n - 1) * cols;  // XC (complex) + FU + TU
+}
+KS_HD size_t smem_bytes(int n, int m) {
+  const int nmax = n > m ? n : m;
+  return (size_t)(n + m) * 16 + (size_t)kWarps * 2 * nmax * 16 + kWarps * 8 * 8;
+}
+
+template <int CLS>
+KS_DEVI bool has_a(int j) { return CLS == KS_ORBIT || CLS == KS_RELATIVE || (CLS == KS_SHIFT_REFLECTION && (j & 1)); }
+template <int CLS>
+KS_DEVI bool has_b(int j) {
+  return CLS == KS_ORBIT || CLS == KS_RELATIVE || CLS == KS_ANTISYMMETRIC || (CLS == KS_SHIFT_REFLECTION && !(j & 1));
+}
+template <int CLS>
+KS_DEVI Tup gload(const double* __restrict__ p, int j, int kp, const Geom& g) {
+  Tup t{0.0, 0.0, 0.0, 0.0};
+  if (CLS == KS_ORBIT || CLS == KS_RELATIVE) {
+    t.a1 = p[j * g.cols + kp];
+    t.b1 = p[j * g.cols + g.k + kp];
+    if (j > 0) {
+      t.a2 = p[(g.h + j) * g.cols + kp];
+      t.b2 = p[(g.h + j) * g.cols + g.k + kp];
+    }
+  } else if (has_a<CLS>(j)) {
+    t.a1 = p[j * g.cols + kp];
+    if (j > 0) t.a2 = p[(g.h + j) * g.cols + kp];
+  } else {
+    t.b1 = p[j * g.cols + kp];
+    if (j > 0) t.b2 = p[(g.h + j) * g.cols + kp];
+  }
+  return t;
+}
+template <int CLS>
+KS_DEVI void gstore(double* __restrict__ p, int j, int kp, const Geom& g, const Tup& t) {
+  if (CLS == KS_ORBIT || CLS == KS_RELATIVE) {
+    p[j * g.cols + kp] = t.a1;
+    p[j * g.cols + g.k + kp] = t.b1;
+    if (j > 0) {
+      p[(g.h + j) * g.cols + kp] = t.a2;
+      p[(g.h + j) * g.cols + g.k + kp] = t.b2;
+    }
+  } else if (has_a<CLS>(j)) {
+    p[j * g.cols + kp] = t.a1;
+    if (j > 0) p[(g.h + j) * g.cols + kp] = t.a2;
+  } else {
+    p[j * g.cols + kp] = t.b1;
+    if (j > 0) p[(g.h + j) * g.cols + kp] = t.b2;
+  }
+}
+template <int CLS>
+KS_DEVI void gproject(Tup& t, int j) {
+  if (!has_a<CLS>(j)) t.a1 = t.a2 = 0.0;
+  if (!has_b<CLS>(j)) t.b1 = t.b2 = 0.0;
+  if (j == 0) t.a2 = t.b2 = 0.0;
+}
+
+KS_DEVI double2 cmul(double2 a, double2 w) { return make_double2(fma(a.x, w.x, -a.y * w.y), fma(a.x, w.y, a.y * w.x)); }
+
+// In-place unnormalised DFT of buf[0..N) by one warp.  tw[j] = exp(-2 pi i j / N).  sign=+1 forward, -1 inverse.
+KS_DEVI void line_fft(double2* buf, double2* tmp, int N, int logN, const double2* __restrict__ tw, int sign, int lane) {
+  __syncwarp();
+  if (logN >= 0) {
+    for (int i = lane; i < N; i += 32) {
+      int r = 0;
+      for (int b = 0; b < logN; ++b) r |= ((i >> b) & 1) << (logN - 1 - b);
+      if (i < r) {
+        const double2 x = buf[i];
+        buf[i] = buf[r];
+        buf[r] = x;
+      }
+    }
+    __syncwarp();
+    for (int len = 2; len <= N; len <<= 1) {
+      const int half = len >> 1, step = N / len;
+      for (int b = lane; b < N / 2; b += 32) {
+        const int grp = b / half, kx = b - grp * half;
+        const int i0 = grp * len + kx, i1 = i0 + half;
+        double2 w = tw[kx * step];
+        if (sign < 0) w.y = -w.y;
+        const double2 x0 = buf[i0], x1 = cmul(buf[i1], w);
+        buf[i0] = make_double2(x0.x + x1.x, x0.y + x1.y);
+        buf[i1] = make_double2(x0.x - x1.x, x0.y - x1.y);
+      }
+      __syncwarp();
+    }
+  } else {
+    for (int kx = lane; kx < N; kx += 32) {
+      double2 acc = make_double2(0.0, 0.0);
+      int idx = 0;
+      for (int t = 0; t < N; ++t) {
+        double2 w = tw[idx];
+        if (sign < 0) w.y = -w.y;
+        const double2 p = cmul(buf[t], w);
+        acc.x += p.x;
+        acc.y += p.y;
+        idx += kx;
+        if (idx >= N) idx -= N;
+      }
+      tmp[kx] = acc;
+    }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) buf[i] = tmp[i];
+    __syncwarp();
+  }
+}
+
+KS_DEVI double warp_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// ---- passes (each executed by the whole CTA, warp per line) -----------------------------------------------------
+// COL inverse from a tuple source: XC[kp][t] <- true spatial modes of the modes-basis array `src`.
+template <int CLS, class TupSrc>
+KS_DEVI void pass_col_inverse(const Geom& g, TupSrc src, double2* XC, double2* line, double2* tmp, const double2* tw_n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int kp = warp; kp < g.k; kp += kWarps) {
+    for (int j = lane; j <= g.h; j += 32) {
+      const Tup t = src(j, kp);
+      if (j == 0) {
+        line[0] = make_double2(ks::kSqrt2 * t.a1, ks::kSqrt2 * t.b1);
+        line[g.n / 2] = make_double2(0.0, 0.0);
+      } else {
+        line[j] = make_double2(t.a1 - t.b2, t.a2 + t.b1);
+        line[g.n - j] = make_double2(t.a1 + t.b2, t.b1 - t.a2);
+      }
+    }
+    line_fft(line, tmp, g.n, g.log_n, tw_n, -1, lane);
+    for (int t = lane; t < g.n; t += 32) XC[(size_t)kp * g.n + t] = make_double2(line[t].x * g.ct, line[t].y * g.ct);
+    __syncwarp();
+  }
+}
+// COL forward: per wavenumber, forward transform then `sink(j, kp, P)` with the true-scaled tuple P.
+// `respec(j, kp, P) -> bool` may return a tuple to write back as inverse-input spectrum (fused second inverse).
+template <int CLS, class Sink>
+KS_DEVI void pass_col_forward(const Geom& g, double2* XC, double2* line, double2* tmp, const double2* tw_n, Sink sink,
+                              bool reinverse) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int kp = warp; kp < g.k; kp += kWarps) {
+    for (int t = lane; t < g.n; t += 32) line[t] = XC[(size_t)kp * g.n + t];
+    line_fft(line, tmp, g.n, g.log_n, tw_n, 1, lane);
+    for (int j = lane; j <= g.h; j += 32) {
+      Tup P;
+      if (j == 0) {
+        const double c0 = ks::kSqrt2 * g.ct;
+        P = Tup{line[0].x * c0, 0.0, line[0].y * c0, 0.0};
+      } else {
+        const double2 y = line[j], z = line[g.n - j];
+        P = Tup{(y.x + z.x) * g.ct, (y.y - z.y) * g.ct, (y.y + z.y) * g.ct, (z.x - y.x) * g.ct};
+      }
+      Tup W{0.0, 0.0, 0.0, 0.0};
+      sink(j, kp, P, W);
+      if (reinverse) {
+        if (j == 0) {
+          line[0] = make_double2(ks::kSqrt2 * W.a1, ks::kSqrt2 * W.b1);
+          line[g.n / 2] = make_double2(0.0, 0.0);
+        } else {
+          line[j] = make_double2(W.a1 - W.b2, W.a2 + W.b1);
+          line[g.n - j] = make_double2(W.a1 + W.b2, W.b1 - W.a2);
+        }
+      }
+    }
+    if (reinverse) {
+      line_fft(line, tmp, g.n, g.log_n, tw_n, -1, lane);
+      for (int t = lane; t < g.n; t += 32) XC[(size_t)kp * g.n + t] = make_double2(line[t].x * g.ct, line[t].y * g.ct);
+    }
+    __syncwarp();
+  }
+}
+// ROW inverse: rows (t, t + n/2) of the field from XC; `emit(t, x, ua, ub)` receives true field values and may
+// return a product pair to be transformed forward again (fused), written back to XC.
+template <class Emit>
+KS_DEVI void pass_row(const Geom& g, double2* XC, double2* line, double2* tmp, const double2* tw_m, bool inverse_first,
+                      bool forward_after, Emit emit) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n2 = g.n / 2;
+  for (int t = warp; t < n2; t += kWarps) {
+    if (inverse_first) {
+      for (int kp = lane; kp < g.k; kp += 32) {
+        const double2 A = XC[(size_t)kp * g.n + t], B = XC[(size_t)kp * g.n + t + n2];
+        line[kp + 1] = make_double2(A.x - B.y, A.y + B.x);
+        line[g.m - kp - 1] = make_double2(A.x + B.y, B.x - A.y);
+      }
+      if (lane == 0) {
+        line[0] = make_double2(0.0, 0.0);
+        line[g.m / 2] = make_double2(0.0, 0.0);
+      }
+      line_fft(line, tmp, g.m, g.log_m, tw_m, -1, lane);
+    }
+    for (int x = lane; x < g.m; x += 32) {
+      double2 v = inverse_first ? make_double2(line[x].x * g.cx, line[x].y * g.cx) : make_double2(0.0, 0.0);
+      emit(t, x, v);  // may replace v by the pair to transform forward
+      line[x] = v;
+    }
+    if (forward_after) {
+      line_fft(line, tmp, g.m, g.log_m, tw_m, 1, lane);
+      for (int kp = lane; kp < g.k; kp += 32) {
+        const double2 y = line[kp + 1], z = line[g.m - kp - 1];
+        XC[(size_t)kp * g.n + t] = make_double2((y.x + z.x) * g.cx, (y.y - z.y) * g.cx);
+        XC[(size_t)kp * g.n + t + n2] = make_double2((y.y + z.y) * g.cx, (z.x - y.x) * g.cx);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int CLS, int OP>
+__global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) {
+  constexpr bool REL = (CLS == KS_RELATIVE);
+  const KsEvalArgs& a = ga.e;
+  const Geom g = ga.g;
+  KS_DYN_SMEM(double2, smem);
+  double2* tw_n = smem;
+  double2* tw_m = smem + g.n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double2* line = smem + g.n + g.m + (size_t)warp * 2 * g.nmax;
+  double2* tmp = line + g.nmax;
+  double* red = reinterpret_cast<double*>(smem + g.n + g.m + (size_t)kWarps * 2 * g.nmax);  // [kWarps][8]
+  for (int i = threadIdx.x; i < g.n; i += kThreads) {
+    double s, c;
+    sincospi(2.0 * i / g.n, &s, &c);
+    tw_n[i] = make_double2(c, -s);
+  }
+  for (int i = threadIdx.x; i < g.m; i += kThreads) {
+    double s, c;
+    sincospi(2.0 * i / g.m, &s, &c);
+    tw_m[i] = make_double2(c, -s);
+  }
+  __syncthreads();
+  double* slot = a.scratch + (size_t)blockIdx.x * ga.slot_doubles;
+  double2* XC = reinterpret_cast<double2*>(slot);
+  double* FU = slot + 2 * (size_t)g.k * g.n;
+  double* TU = FU + (size_t)g.n * g.m;
+  const int n2 = g.n / 2;
+  const bool fix_t = a.cmask & KS_FIX_T, fix_x = a.cmask & KS_FIX_X, fix_s = (a.cmask & KS_FIX_S) || !REL;
+
+  for (int orbit = blockIdx.x; orbit < a.batch; orbit += gridDim.x) {
+    if constexpr (OP == KS_OP_TRANSFORM) {
+      const int fb = ga.from_basis, tb = ga.to_basis;
+      const size_t in_size = fb == 0 ? (size_t)g.n * g.m : fb == 1 ? (size_t)g.n * 2 * g.k : (size_t)g.nm;
+      const size_t out_size = tb == 0 ? (size_t)g.n * g.m : tb == 1 ? (size_t)g.n * 2 * g.k : (size_t)g.nm;
+      const double* in = ga.tin + (size_t)orbit * in_size;
+      double* out = ga.tout + (size_t)orbit * out_size;
+      // stage 1: reach the complex spatial-mode array XC
+      if (fb == 2) {
+        pass_col_inverse<CLS>(g, [&](int j, int kp) { return gload<CLS>(in, j, kp, g); }, XC, line, tmp, tw_n);
+      } else if (fb == 1) {
+        for (int i = threadIdx.x; i < g.n * g.k; i += kThreads) {
+          const int t = i / g.k, kp = i - t * g.k;
+          XC[(size_t)kp * g.n + t] = make_double2(in[(size_t)t * 2 * g.k + kp], in[(size_t)t * 2 * g.k + g.k + kp]);
+        }
+      } else {
+        pass_row(g, XC, line, tmp, tw_m, false, true, [&](int t, int x, double2& v) {
+          v = make_double2(in[(size_t)t * g.m + x], in[(size_t)(t + n2) * g.m + x]);
+        });
+      }
+      __syncthreads();
+      // stage 2: leave it
+      if (tb == 0) {
+        pass_row(g, XC, line, tmp, tw_m, true, false, [&](int t, int x, double2& v) {
+          out[(size_t)t * g.m + x] = v.x;
+          out[(size_t)(t + n2) * g.m + x] = v.y;
+        });
+      } else if (tb == 1) {
+        for (int i = threadIdx.x; i < g.n * g.k; i += kThreads) {
+          const int t = i / g.k, kp = i - t * g.k;
+          const double2 v = XC[(size_t)kp * g.n + t];
+          out[(size_t)t * 2 * g.k + kp] = v.x;
+          out[(size_t)t * 2 * g.k + g.k + kp] = v.y;
+        }
+      } else {
+        pass_col_forward<CLS>(g, XC, line, tmp, tw_n, [&](int j, int kp, Tup P, Tup&) {
+          gproject<CLS>(P, j);
+          gstore<CLS>(out, j, kp, g, P);
+        }, false);
+      }
+      __syncthreads();
+      continue;
+    } else {
+      const double* Mo = a.modes + (size_t)orbit * g.nm;
+      const double* Vo = (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) ? a.vmodes + (size_t)orbit * g.nm : nullptr;
+      double* Oo = a.out_state + (size_t)orbit * g.nm;
+      double* Fo = (OP == KS_OP_COSTGRAD) ? (a.f_out ? a.f_out + (size_t)orbit * g.nm : TU) : Oo;
+      const double T = a.params[orbit * 3 + 0], Lx = a.params[orbit * 3 + 1], S = a.params[orbit * 3 + 2];
+      const double wbase = -1.0 * (ks::kTwoPi * g.n / T), qbase = ks::kTwoPi * g.m / Lx;
+      const double sig = REL ? S / T : 0.0;
+      const bool need_nuu = (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) || !fix_x;
+      double vt = 0.0, vx = 0.0, vs = 0.0;
+      if constexpr (OP == KS_OP_MATVEC) {
+        vt = fix_t ? 0.0 : a.vparams[orbit * 3 + 0] * (-1.0 / T);
+        vx = fix_x ? 0.0 : a.vparams[orbit * 3 + 1] * (1.0 / Lx);
+        vs = fix_s ? 0.0 : a.vparams[orbit * 3 + 2] * (-1.0 / T);
+      }
+      // A: u modes -> XC
+      pass_col_inverse<CLS>(g, [&](int j, int kp) { return gload<CLS>(Mo, j, kp, g); }, XC, line, tmp, tw_n);
+      __syncthreads();
+      // B: XC -> field u (kept in FU); u^2 -> XC
+      pass_row(g, XC, line, tmp, tw_m, true, need_nuu, [&](int t, int x, double2& v) {
+        FU[(size_t)t * g.m + x] = v.x;
+        FU[(size_t)(t + n2) * g.m + x] = v.y;
+        v = make_double2(v.x * v.x, v.y * v.y);
+      });
+      __syncthreads();
+      // C: tuple stage 1 (+ fused second inverse)
+      double s_ff = 0.0, s_x = 0.0, s_d = 0.0, s_e = 0.0;
+      if (!need_nuu) {
+        for (int i = threadIdx.x; i < g.k * g.n; i += kThreads) XC[i] = make_double2(0.0, 0.0);
+        __syncthreads();
+      }
+      pass_col_forward<CLS>(g, XC, line, tmp, tw_n, [&](int j, int kp, Tup P, Tup& W) {
+        const double w = (j == 0) ? 0.0 : wbase * (j * (1.0 / g.n));
+        const double q = qbase * ((kp + 1) * (1.0 / g.m));
+        const double q2 = q * q, q4 = q2 * q2, d = q4 - q2, e = 2.0 * q2 - 4.0 * q4;
+        const double qn = 0.5 * q;
+        Tup N{-qn * P.b1, -qn * P.b2, qn * P.a1, qn * P.a2};
+        gproject<CLS>(N, j);
+        const Tup Mt = gload<CLS>(Mo, j, kp, g);
+        if constexpr (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) {
+          Tup F;
+          F.a1 = fma(d, Mt.a1, fma(-w, Mt.a2, N.a1));
+          F.a2 = fma(d, Mt.a2, fma(w, Mt.a1, N.a2));
+          F.b1 = fma(d, Mt.b1, fma(-w, Mt.b2, N.b1));
+          F.b2 = fma(d, Mt.b2, fma(w, Mt.b1, N.b2));
+          if constexpr (REL) {
+            const double sq = sig * q;
+            F.a1 = fma(sq, Mt.b1, F.a1);
+            F.a2 = fma(sq, Mt.b2, F.a2);
+            F.b1 = fma(-sq, Mt.a1, F.b1);
+            F.b2 = fma(-sq, Mt.a2, F.b2);
+          }
+          gproject<CLS>(F, j);
+          const double ff = dot_tup(F, F);
+          s_ff += ff;
+          gstore<CLS>(Fo, j, kp, g, F);
+          if constexpr (OP == KS_OP_COSTGRAD) {
+            const double mf = dot_tup(Mt, F), xt = w * rot_t(Mt, F);
+            s_e += fma(e + d, mf, xt - ff);
+            s_x += xt;
+            if constexpr (REL) s_d += q * rot_x(Mt, F);
+            W = dx_tup(F, q);
+          }
+        } else if constexpr (OP == KS_OP_RMATVEC) {
+          const Tup V = gload<CLS>(Vo, j, kp, g);
+          const double dd = REL ? q * rot_x(Mt, V) : 0.0;
+          s_e += fma(e, dot_tup(Mt, V), fma(sig, dd, -dot_tup(N, V)));
+          s_x += w * rot_t(Mt, V);
+          s_d += dd;
+          W = dx_tup(V, q);
+        } else {
+          const Tup V = gload<CLS>(Vo, j, kp, g);
+          const double cdx = REL ? (-sig * vt + sig * vx + vs) * q : 0.0, cdt = vt * w, ce = vx * e;
+          Tup R;
+          R.a1 = fma(d, V.a1, -w * V.a2);
+          R.a2 = fma(d, V.a2, w * V.a1);
+          R.b1 = fma(d, V.b1, -w * V.b2);
+          R.b2 = fma(d, V.b2, w * V.b1);
+          if constexpr (REL) {
+            const double sq = sig * q;
+            R.a1 = fma(sq, V.b1, R.a1);
+            R.a2 = fma(sq, V.b2, R.a2);
+            R.b1 = fma(-sq, V.a1, R.b1);
+            R.b2 = fma(-sq, V.a2, R.b2);
+          }
+          R.a1 += fma(ce, Mt.a1, fma(-cdt, Mt.a2, fma(-cdx, Mt.b1, -vx * N.a1)));
+          R.a2 += fma(ce, Mt.a2, fma(cdt, Mt.a1, fma(-cdx, Mt.b2, -vx * N.a2)));
+          R.b1 += fma(ce, Mt.b1, fma(-cdt, Mt.b2, fma(cdx, Mt.a1, -vx * N.b1)));
+          R.b2 += fma(ce, Mt.b2, fma(cdt, Mt.b1, fma(cdx, Mt.a2, -vx * N.b2)));
+          gproject<CLS>(R, j);
+          gstore<CLS>(Fo, j, kp, g, R);
+          W = V;
+        }
+      }, OP != KS_OP_EQN);
+      // deterministic CTA reduction of the scalar sums
+      {
+        const double r0 = warp_sum(s_ff), r1 = warp_sum(s_e), r2 = warp_sum(fma(-sig, s_d, s_x)), r3 = warp_sum(s_d);
+        if (lane == 0) {
+          red[warp * 8 + 0] = r0;
+          red[warp * 8 + 1] = r1;
+          red[warp * 8 + 2] = r2;
+          red[warp * 8 + 3] = r3;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+          for (int wq = 0; wq < kWarps; ++wq) {
+            t0 += red[wq * 8 + 0];
+            t1 += red[wq * 8 + 1];
+            t2 += red[wq * 8 + 2];
+            t3 += red[wq * 8 + 3];
+          }
+          if ((OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) && a.out_cost) a.out_cost[orbit] = 0.5 * t0;
+          if ((OP == KS_OP_COSTGRAD || OP == KS_OP_RMATVEC) && a.out_params) {
+            double gt = fix_t ? 0.0 : (-1.0 / T) * t2, gx = fix_x ? 0.0 : (1.0 / Lx) * t1, gs = fix_s ? 0.0 : (-1.0 / T) * t3;
+            if (OP == KS_OP_COSTGRAD && a.precond) {
+              if (!fix_t) gt *= 1.0 / T;
+              if (!fix_x) gx *= 1.0 / ((Lx * Lx) * (Lx * Lx));
+            }
+            a.out_params[orbit * 3 + 0] = gt;
+            a.out_params[orbit * 3 + 1] = gx;
+            a.out_params[orbit * 3 + 2] = gs;
+          }
+        }
+      }
+      __syncthreads();
+      if constexpr (OP == KS_OP_EQN) continue;
+      // D: second field times u -> XC
+      pass_row(g, XC, line, tmp, tw_m, true, true, [&](int t, int x, double2& v) {
+        v = make_double2(v.x * FU[(size_t)t * g.m + x], v.y * FU[(size_t)(t + n2) * g.m + x]);
+      });
+      __syncthreads();
+      // E: tuple stage 2
+      pass_col_forward<CLS>(g, XC, line, tmp, tw_n, [&](int j, int kp, Tup P, Tup&) {
+        const double w = (j == 0) ? 0.0 : wbase * (j * (1.0 / g.n));
+        const double q = qbase * ((kp + 1) * (1.0 / g.m));
+        const double q2 = q * q, q4 = q2 * q2, d = q4 - q2;
+        Tup R;
+        if constexpr (OP == KS_OP_MATVEC) {
+          const Tup A0 = gload<CLS>(Fo, j, kp, g);
+          R = Tup{fma(-q, P.b1, A0.a1), fma(-q, P.b2, A0.a2), fma(q, P.a1, A0.b1), fma(q, P.a2, A0.b2)};
+        } else {
+          const Tup V = (OP == KS_OP_COSTGRAD) ? gload<CLS>(Fo, j, kp, g) : gload<CLS>(Vo, j, kp, g);
+          R.a1 = fma(d, V.a1, fma(w, V.a2, -P.a1));
+          R.a2 = fma(d, V.a2, fma(-w, V.a1, -P.a2));
+          R.b1 = fma(d, V.b1, fma(w, V.b2, -P.b1));
+          R.b2 = fma(d, V.b2, fma(-w, V.b1, -P.b2));
+          if constexpr (REL) {
+            const double sq = sig * q;
+            R.a1 = fma(-sq, V.b1, R.a1);
+            R.a2 = fma(-sq, V.b2, R.a2);
+            R.b1 = fma(sq, V.a1, R.b1);
+            R.b2 = fma(sq, V.a2, R.b2);
+          }
+          if (OP == KS_OP_COSTGRAD && a.precond) {
+            const double pm = 1.0 / ((w < 0 ? -w : w) + q2 + q4);
+            R.a1 *= pm; R.a2 *= pm; R.b1 *= pm; R.b2 *= pm;
+          }
+        }
+        gproject<CLS>(R, j);
+        gstore<CLS>(Oo, j, kp, g, R);
+      }, false);
+      __syncthreads();
+    }
+  }
+}
+
+// OrbitKS.precondition (ks/orbits.py:1034-1089) as a standalone elementwise op: out = in / (|w_j| + q^2 + q^4),
+// t <- t * T^-pexp_t, x <- x * L^-pexp_x for unconstrained parameters, s untouched.
+struct PrecArgs {
+  const double* in;
+  const double* gp_in;
+  const double* params;
+  double* out;
+  double* gp_out;
+  int batch, n, m, cols;
+  unsigned cmask;
+  double pexp_t, pexp_x;
+};
+__global__ void ks_precondition_kernel(const PrecArgs a) {
+  const int orbit = blockIdx.y;
+  const int nm = (a.n - 1) * a.cols, h = a.n / 2 - 1, k = a.m / 2 - 1;
+  const double T = a.params[orbit * 3 + 0], Lx = a.params[orbit * 3 + 1];
+  const double wbase = -1.0 * (ks::kTwoPi * a.n / T), qbase = ks::kTwoPi * a.m / Lx;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nm; i += gridDim.x * blockDim.x) {
+    const int r = i / a.cols, c = i - r * a.cols;
+    const int j = r <= h ? r : r - h, kp = c < k ? c : c - k;
+    const double w = wbase * (j * (1.0 / a.n)), q = qbase * ((kp + 1) * (1.0 / a.m));
+    const double q2 = q * q;
+    a.out[(size_t)orbit * nm + i] = a.in[(size_t)orbit * nm + i] * (1.0 / ((w < 0 ? -w : w) + q2 + q2 * q2));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.gp_out) {
+    double gt = a.gp_in[orbit * 3 + 0], gx = a.gp_in[orbit * 3 + 1];
+    if (!(a.cmask & KS_FIX_T)) gt *= pow(T, -a.pexp_t);
+    if (!(a.cmask & KS_FIX_X)) gx *= pow(Lx, -a.pexp_x);
+    a.gp_out[orbit * 3 + 0] = gt;
+    a.gp_out[orbit * 3 + 1] = gx;
+    a.gp_out[orbit * 3 + 2] = a.gp_in[orbit * 3 + 2];
+  }
+}
+
+}  // namespace ksg

@@ -1,0 +1,428 @@
+"""Single-orbit drop-in classes: OrbitKS, RelativeOrbitKS, ShiftReflectionOrbitKS, AntisymmetricOrbitKS.
+
+Same constructor, attribute and method names as the reference's equation plugin (orbithunter/ks/orbits.py:24,
+:2554, :3582, :3189 and the generic container orbithunter/core.py:10) for the hot path named by the north star:
+``transform, eqn, matvec, rmatvec, cost, costgrad, precondition, cdof, constants, from_numpy_array, increment,
+dot, norm, jacobian, populate``.  State and parameters are host objects (NumPy array, tuple of floats) exactly as in
+the reference; every numerical method uploads a batch of one to the GPU, runs the same libks_b200.so kernels the
+batched container uses, and returns a new instance.  There is no NumPy implementation behind these methods.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import torch
+
+from .batch import BatchedOrbitKS, basis_shape
+
+_TWO_PI = 2 * np.pi
+
+
+class OrbitKS:
+    _cls_name = "OrbitKS"
+
+    # ---- static description (reference ks/orbits.py:138-229, :1717-1736) ---------------------------------------
+    @staticmethod
+    def bases_labels():
+        return "field", "spatial_modes", "modes"
+
+    @staticmethod
+    def parameter_labels():
+        return "t", "x", "s"
+
+    @staticmethod
+    def discretization_labels():
+        return "n", "m"
+
+    @staticmethod
+    def dimension_labels():
+        return "t", "x"
+
+    @staticmethod
+    def minimal_shape():
+        return 2, 4
+
+    @staticmethod
+    def minimal_shape_increments():
+        return 2, 2
+
+    @staticmethod
+    def _default_shape():
+        return 32, 32
+
+    @classmethod
+    def _default_parameter_ranges(cls):
+        return {"t": (20, 200), "x": (20, 100)}
+
+    @classmethod
+    def _default_constraints(cls):
+        return {"t": False, "x": False, "s": True}
+
+    def periodic_dimensions(self):
+        return True, True
+
+    # ---- construction (core.py:111-134, ks/orbits.py:100-120, :1851-1897) ----------------------------------------
+    def __init__(self, state=None, basis=None, parameters=None, discretization=None, constraints=None, **kwargs):
+        if state is None or basis is None or discretization is None:
+            self._parse_state(state, basis)
+        else:
+            self.state, self.basis, self.discretization = state, basis, tuple(discretization)
+        if parameters is None or constraints is None:
+            self._parse_parameters(parameters, constraints)
+        else:
+            self.parameters, self.constraints = parameters, constraints
+        if self.parameters:
+            self.parameters = tuple(float(p) for p in self.parameters)
+        self._workers = kwargs.get("_workers", 1)
+
+    def _mode_discretization(self, shape):
+        return shape[0] + 1, shape[1] + 2
+
+    def _parse_state(self, state, basis):
+        if isinstance(state, np.ndarray):
+            if state.ndim != 2:
+                raise ValueError('"state" array must be two-dimensional')
+            self.state = state
+        else:
+            self.state = np.array([], dtype=float).reshape(0, 0)
+        if self.state.size > 0:
+            if basis is None:
+                raise ValueError("basis must be provided when state is provided")
+            if basis == "modes":
+                n, m = self._mode_discretization(self.state.shape)
+            elif basis == "field":
+                n, m = self.state.shape
+            elif basis == "spatial_modes":
+                n, m = self.state.shape[0], self.state.shape[1] + 2
+            else:
+                raise ValueError('basis not recognized; must equal "field" or "spatial_modes", or "modes"')
+            if n < self.minimal_shape()[0] or m < self.minimal_shape()[1]:
+                warnings.warn("\nminimum discretization requirements not met; methods may not work as intended.", RuntimeWarning)
+            self.basis, self.discretization = basis, (n, m)
+        else:
+            self.basis, self.discretization = None, None
+
+    def _parse_parameters(self, parameters, constraints):
+        defaults = self._default_constraints()
+        given = defaults if constraints is None else constraints
+        self.constraints = {k: (given.get(k, True) if k in defaults else True) for k in self.parameter_labels()}
+        if parameters is None:
+            self.parameters = None
+        elif isinstance(parameters, tuple):
+            labels = self.parameter_labels()
+            vals = list(parameters)[: len(labels)]
+            self.parameters = tuple(vals + [0] * (len(labels) - len(vals)))
+        else:
+            raise TypeError('"parameters" is required to be a tuple or NoneType. singleton parameters need to be cast as tuple (val,).')
+
+    def __getattr__(self, attr):
+        if attr.startswith("__"):
+            raise AttributeError(attr)
+        if attr in ("t", "x", "s"):
+            params = self.__dict__.get("parameters")
+            if params is None:
+                raise AttributeError(f"Cannot retrieve '{attr}' when parameters attribute is NoneType")
+            return params["txs".index(attr)]
+        if attr in ("n", "m"):
+            disc = self.__dict__.get("discretization")
+            if disc is None:
+                raise AttributeError(f"Cannot retrieve '{attr}' when discretization attribute is NoneType")
+            return disc["nm".index(attr)]
+        raise AttributeError(f"{self.__class__.__name__} has no attribute {attr}")
+
+    def __str__(self):
+        return self.__class__.__name__
+
+    def __repr__(self):
+        p = None if self.parameters is None else tuple(round(float(x), 3) for x in self.parameters)
+        return f'{self.__class__.__name__}({{"shape": {list(self.shape)}, "basis": "{self.basis}", "(t, x, s)": {p}}})'
+
+    @property
+    def shape(self):
+        return self.state.shape
+
+    @property
+    def size(self):
+        return self.state.size
+
+    @property
+    def ndim(self):
+        return self.state.ndim
+
+    def shapes(self):
+        n, m = self.discretization
+        return tuple(basis_shape(self._cls_id(), n, m, b) for b in self.bases_labels())
+
+    def dimensions(self):
+        return self.t, self.x
+
+    def copy(self):
+        return self.__class__(**{k: (v.copy() if hasattr(v, "copy") else v) for k, v in vars(self).items()})
+
+    def _new(self, **changes):
+        return self.__class__(**{**vars(self), **changes})
+
+    @classmethod
+    def _cls_id(cls):
+        from .batch import CLASS_IDS
+
+        return CLASS_IDS[cls._cls_name]
+
+    # ---- device round trip ---------------------------------------------------------------------------------------
+    def _batched(self, state=None, basis=None, parameters=None):
+        st = self.state if state is None else state
+        pr = self.parameters if parameters is None else parameters
+        return BatchedOrbitKS(torch.as_tensor(np.ascontiguousarray(st, dtype=np.float64)[None]),
+                              torch.as_tensor(np.asarray(pr, dtype=np.float64)[None]), self._cls_id(),
+                              self.basis if basis is None else basis, self.discretization, self.constraints)
+
+    @staticmethod
+    def _host(t):
+        return t[0].cpu().numpy()
+
+    # ---- arithmetic (core.py:136-451) ----------------------------------------------------------------------------
+    def _other(self, other):
+        return other.state if isinstance(other, OrbitKS) else other
+
+    def __add__(self, other):
+        return self._new(state=self.state + self._other(other))
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self._new(state=self.state - self._other(other))
+
+    def __rsub__(self, other):
+        return self._new(state=self._other(other) - self.state)
+
+    def __mul__(self, other):
+        return self._new(state=np.multiply(self.state, self._other(other)))
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        return self._new(state=np.divide(self.state, self._other(other)))
+
+    def __neg__(self):
+        return self._new(state=-self.state)
+
+    def dot(self, other):
+        return float(np.dot(self.state.ravel(), other.state.ravel()))
+
+    def norm(self, order=None):
+        return np.linalg.norm(self.state.ravel(), ord=order)
+
+    # ---- transforms (ks/orbits.py:231-303) -----------------------------------------------------------------------
+    def transform(self, to=None, array=False, inplace=False):
+        if self.state is None or self.state.size == 0:
+            raise ValueError(f"Trying to transform an unpopulated {self} instance.")
+        if self.basis is None:
+            raise ValueError("Trying to transform state with unknown basis")
+        if to not in self.bases_labels():
+            raise ValueError("Trying to transform to unrecognized basis.")
+        if to == self.basis:
+            return self.state if array else self
+        out = self._host(self._batched().transform(to).state)
+        if inplace:
+            self.state, self.basis = out, to
+            return self.state if array else self
+        return out if array else self._new(state=out, basis=to)
+
+    # ---- governing equation and its linearisations ------------------------------------------------------------------
+    def eqn(self, **kwargs):
+        assert self.basis == "modes", "Convert to spatiotemporal Fourier mode basis before computing K-S equation DAEs."
+        return self._new(state=self._host(self._batched().eqn().state))
+
+    def cost(self, evaleqn=True):
+        if evaleqn:
+            return float(self.transform(to="modes")._batched().cost()[0].item())
+        v = self.state.ravel()
+        return 0.5 * float(v.dot(v))
+
+    def matvec(self, other, **kwargs):
+        assert (self.basis == "modes") and (other.basis == "modes")
+        vb = self._batched(state=other.state, parameters=other.parameters)
+        return self._new(state=self._host(self._batched().matvec(vb).state))
+
+    def rmatvec(self, other, **kwargs):
+        assert (self.basis == "modes") and (other.basis == "modes")
+        r = self._batched().rmatvec(self._batched(state=other.state))
+        return self._new(state=self._host(r.state), parameters=tuple(float(x) for x in self._host(r.parameters)))
+
+    def costgrad(self, *args, **kwargs):
+        """J^T F (ks/orbits.py:757-791).  With no argument F is evaluated and the fused kernel is used."""
+        pc = bool(kwargs.get("preconditioning", False))
+        if args and args[0] is not None:
+            grad = self.rmatvec(args[0])
+            if pc:
+                grad = grad.precondition(**{"pmult": self.preconditioning_parameters(), **kwargs})
+            return grad
+        _, g = self._batched().costgrad(preconditioning=pc)
+        return self._new(state=self._host(g.state), parameters=tuple(float(x) for x in self._host(g.parameters)))
+
+    def preconditioning_parameters(self):
+        return (self.t, self.n), (self.x, self.m)
+
+    def precondition(self, **kwargs):
+        """Diagonal rescaling 1/(|w| + q^2 + q^4), t/T, x/L^4 (ks/orbits.py:1034-1089), on the device."""
+        (T, n), (L, m) = kwargs.get("pmult", self.preconditioning_parameters())
+        if (n, m) != tuple(self.discretization):
+            raise ValueError("pmult discretization must match the orbit being preconditioned")
+        ref = torch.tensor([[float(T), float(L), 0.0]], dtype=torch.float64, device="cuda")
+        r = self._batched(basis="modes").precondition(ref, kwargs.get("pexp", (1, 4)))
+        return self._new(state=self._host(r.state), basis="modes", parameters=tuple(float(x) for x in self._host(r.parameters)))
+
+    def jacobian(self, **kwargs):
+        """Dense (Nm x cdof) Jacobian (ks/orbits.py:557-657): one batched matvec over the identity, on the GPU."""
+        assert self.basis == "modes", "Convert to spatiotemporal Fourier mode basis before computing Jacobian"
+        nm = self.state.size
+        free = [i for i, lab in enumerate(self.parameter_labels()) if not self.constraints[lab]]
+        ncol = nm + len(free)
+        v = np.zeros((ncol, nm))
+        v[np.arange(nm), np.arange(nm)] = 1.0
+        vp = np.zeros((ncol, 3))
+        for slot, i in enumerate(free):
+            vp[nm + slot, i] = 1.0
+        ub = BatchedOrbitKS(torch.as_tensor(np.broadcast_to(self.state, (ncol,) + self.state.shape).copy()),
+                            torch.as_tensor(np.broadcast_to(np.asarray(self.parameters), (ncol, 3)).copy()), self._cls_id(),
+                            "modes", self.discretization, self.constraints)
+        vb = BatchedOrbitKS(torch.as_tensor(v.reshape((ncol,) + self.state.shape)), torch.as_tensor(vp), self._cls_id(), "modes",
+                            self.discretization, self.constraints)
+        return ub.matvec(vb).state.reshape(ncol, nm).T.contiguous().cpu().numpy()
+
+    # ---- vector packing (core.py:1617-1664, :1760-1796; ks/orbits.py:305-377) ----------------------------------------
+    def cdof(self):
+        free = tuple(p for p, lab in zip(self.parameters or (), self.parameter_labels()) if not self.constraints[lab])
+        return np.concatenate((self.state.ravel(), free), axis=0).reshape(-1, 1)
+
+    def constants(self):
+        return tuple(p for p, lab in zip(self.parameters or (), self.parameter_labels()) if self.constraints[lab])
+
+    def orbit_vector(self):
+        return np.concatenate((self.state.ravel(), tuple(self.parameters or ())), axis=0).reshape(-1, 1)
+
+    def from_numpy_array(self, cdof, *args, **kwargs):
+        flat = np.asarray(cdof).ravel()
+        free = [float(p) for p in flat[self.size:].real]
+        const = list(args)
+        params = None
+        if self.parameters is not None:
+            vals = []
+            for lab in self.parameter_labels():
+                if not self.constraints.get(lab, True) and free:
+                    vals.append(free.pop(0))
+                else:
+                    vals.append(float(const.pop(0)) if const else 0.0)
+            params = tuple(vals)
+        return self._new(state=np.reshape(flat[: self.size], self.shape), parameters=params, **kwargs)
+
+    def increment(self, other, step_size=1, **kwargs):
+        params = None
+        if self.parameters is not None:
+            params = tuple(a + step_size * b for a, b in zip(self.parameters, other.parameters))
+        return self.__class__(**{**vars(self), **kwargs, "state": self.state + step_size * other.state, "parameters": params})
+
+    # ---- seeds (ks/orbits.py:1738-1849, core.py:2016-2044, :2434-2514; default modulations only) ----------------------
+    def populate(self, attr="all", **kwargs):
+        if attr in ("all", "parameters"):
+            self._populate_parameters(**kwargs)
+        if attr in ("all", "state"):
+            if self.size == 0 or kwargs.get("overwrite", False):
+                self._populate_state(**kwargs)
+            else:
+                raise ValueError(" overwriting a non-empty state requires overwrite=True. ")
+        return self
+
+    def _populate_parameters(self, **kwargs):
+        if isinstance(kwargs.get("seed", None), int):
+            np.random.seed(kwargs["seed"])
+        ranges = kwargs.get("parameter_ranges", self._default_parameter_ranges())
+        current = list(self.parameters or [None] * 3)[:3] + [None] * (3 - len(self.parameters or [None] * 3))
+        out = []
+        for lab, val in zip(self.parameter_labels(), current):
+            gen = ranges.get(lab, (0, 0))
+            if kwargs.get("overwrite", False) or val is None:
+                if isinstance(gen, tuple) and len(gen) == 2:
+                    val = gen[0] + (gen[1] - gen[0]) * np.random.rand()
+                elif np.isscalar(gen):
+                    val = gen
+                else:
+                    val = gen[np.random.choice(range(len(gen)))]
+            out.append(float(val))
+        self.parameters = tuple(out)
+
+    def _populate_state(self, **kwargs):
+        T, L = self.t, self.x
+        if kwargs.get("spatial_modulation", "laplace") != "laplace" or kwargs.get("temporal_modulation", "gaussian") != "gaussian":
+            raise NotImplementedError("only the reference's default modulations ('laplace' space, 'gaussian' time) are provided")
+        tscale = kwargs.get("tscale", int(np.round(T / 20.0)))
+        xscale = kwargs.get("xscale", int(np.round(L / (_TWO_PI * np.sqrt(2)))))
+        xvar = kwargs.get("xvar", max([np.sqrt(xscale), 1]))
+        tvar = kwargs.get("tvar", max([np.sqrt(tscale), 1]))
+        np.random.seed(kwargs.get("seed", None))  # legacy global MT19937 stream, as in the reference
+        n, m = kwargs.get("discretization", None) or self.discretization or self._default_shape()
+        self.discretization = (int(n), int(m))
+        rows, cols = self.shapes()[2]
+        kx = np.arange(1, m // 2)
+        space_ = np.concatenate((kx, kx))[None, :cols]
+        jt = np.arange(1, n // 2)
+        time_ = np.concatenate(([0], jt, jt))[:, None]
+        random_modes = np.random.randn(rows, cols)
+        norm0 = np.linalg.norm(random_modes)
+        modes = np.exp(-1.0 * np.abs(space_ - (xscale + np.sqrt(time_))) / np.sqrt(xvar)) * random_modes
+        modes = np.exp(-((time_ - tscale) ** 2) / (2 * tvar)) * modes
+        self.state = (norm0 / np.linalg.norm(modes)) * modes
+        self.basis = "modes"
+
+
+class RelativeOrbitKS(OrbitKS):
+    _cls_name = "RelativeOrbitKS"
+
+    def __init__(self, state=None, basis=None, parameters=None, discretization=None, constraints=None, frame="comoving",
+                 **kwargs):
+        self.frame = frame
+        super().__init__(state=state, basis=basis, parameters=parameters, discretization=discretization,
+                         constraints=constraints, **kwargs)
+
+    @classmethod
+    def _default_parameter_ranges(cls):
+        return {"t": (20, 200), "x": (20, 100), "s": (0, 0)}
+
+    @classmethod
+    def _default_constraints(cls):
+        return {"t": False, "x": False, "s": False}
+
+    def periodic_dimensions(self):
+        return (True, True) if self.frame == "comoving" else (False, True)
+
+    def populate(self, attr="all", **kwargs):
+        # the reference resets S to 0 unless it estimates a shift from an existing state (ks/orbits.py:2872-2883);
+        # shift estimation (calculate_spatial_shift, fsolve on the host) is outside the hot path.
+        super().populate(attr=attr, **kwargs)
+        self.parameters = (self.parameters[0], self.parameters[1], 0.0)
+        return self
+
+
+class _HalfColumnMixin:
+    def _mode_discretization(self, shape):
+        return shape[0] + 1, 2 * shape[1] + 2
+
+
+class ShiftReflectionOrbitKS(_HalfColumnMixin, OrbitKS):
+    _cls_name = "ShiftReflectionOrbitKS"
+
+
+class AntisymmetricOrbitKS(_HalfColumnMixin, OrbitKS):
+    _cls_name = "AntisymmetricOrbitKS"
+
+    @staticmethod
+    def _default_shape():
+        return 1, 32
+
+    @classmethod
+    def _default_parameter_ranges(cls):
+        return {"t": (20.0, 200.0), "x": (38.5, 100.0)}
+
+
+CLASSES = {c._cls_name: c for c in (OrbitKS, RelativeOrbitKS, ShiftReflectionOrbitKS, AntisymmetricOrbitKS)}

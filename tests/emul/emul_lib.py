@@ -1,0 +1,104 @@
+"""Load the CPU-thread emulation build of the kernels and call its C ABI with NumPy (host) pointers -- tests only."""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        spec = importlib.util.spec_from_file_location("build_emul", os.path.join(HERE, "build_emul.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        path = mod.build()
+        spec2 = importlib.util.spec_from_file_location("_cabi", os.path.join(ROOT, "orbithunter_b200", "_cabi.py"))
+        cabi = importlib.util.module_from_spec(spec2)
+        spec2.loader.exec_module(cabi)
+        _lib = cabi.bind(C.CDLL(path))
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def _ws(L, cls, n, m, B):
+    nbytes = L.ks_workspace_bytes(cls, n, m, B)
+    return np.zeros(max(nbytes // 8, 1)), nbytes
+
+
+def _chk(L, rc):
+    if rc != 0:
+        raise RuntimeError(f"ks error {rc}: {L.ks_last_error().decode()}")
+
+
+def mode_shape(cls, n, m):
+    return (n - 1, m - 2) if cls in (0, 1) else (n - 1, m // 2 - 1)
+
+
+def basis_shape(cls, n, m, basis):
+    return {0: (n, m), 1: (n, m - 2), 2: mode_shape(cls, n, m)}[basis]
+
+
+def transform(cls, n, m, arr, frm, to):
+    L = lib()
+    arr = np.ascontiguousarray(arr, dtype=float)
+    B = arr.shape[0]
+    out = np.zeros((B,) + basis_shape(cls, n, m, to))
+    ws, nb = _ws(L, cls, n, m, B)
+    _chk(L, L.ks_transform(cls, n, m, B, frm, to, _p(arr), _p(out), _p(ws), nb, None))
+    return out
+
+
+def eqn(cls, n, m, modes, params):
+    L = lib()
+    modes = np.ascontiguousarray(modes, dtype=float)
+    params = np.ascontiguousarray(params, dtype=float)
+    B = modes.shape[0]
+    F = np.zeros_like(modes)
+    cost = np.zeros(B)
+    ws, nb = _ws(L, cls, n, m, B)
+    _chk(L, L.ks_eqn(cls, n, m, B, _p(modes), _p(params), _p(F), _p(cost), _p(ws), nb, None))
+    return F, cost
+
+
+def matvec(cls, n, m, modes, params, v, vp, cmask):
+    L = lib()
+    modes, params, v, vp = (np.ascontiguousarray(x, dtype=float) for x in (modes, params, v, vp))
+    B = modes.shape[0]
+    out = np.zeros_like(modes)
+    ws, nb = _ws(L, cls, n, m, B)
+    _chk(L, L.ks_matvec(cls, n, m, B, _p(modes), _p(params), _p(v), _p(vp), cmask, _p(out), _p(ws), nb, None))
+    return out
+
+
+def rmatvec(cls, n, m, modes, params, v, cmask):
+    L = lib()
+    modes, params, v = (np.ascontiguousarray(x, dtype=float) for x in (modes, params, v))
+    B = modes.shape[0]
+    out = np.zeros_like(modes)
+    op = np.zeros((B, 3))
+    ws, nb = _ws(L, cls, n, m, B)
+    _chk(L, L.ks_rmatvec(cls, n, m, B, _p(modes), _p(params), _p(v), cmask, _p(out), _p(op), _p(ws), nb, None))
+    return out, op
+
+
+def costgrad(cls, n, m, modes, params, cmask, precond=False, want_f=True):
+    L = lib()
+    modes, params = (np.ascontiguousarray(x, dtype=float) for x in (modes, params))
+    B = modes.shape[0]
+    g = np.zeros_like(modes)
+    gp = np.zeros((B, 3))
+    cost = np.zeros(B)
+    F = np.zeros_like(modes) if want_f else None
+    ws, nb = _ws(L, cls, n, m, B)
+    _chk(L, L.ks_costgrad(cls, n, m, B, _p(modes), _p(params), cmask, int(precond), _p(cost), _p(g), _p(gp), _p(F), _p(ws),
+                          nb, None))
+    return cost, g, gp, F
