@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--sets", type=int, default=4, help="distinct input/output sets rotated to exceed L2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=None, help="tuning: warp32 kernel variant (ks_debug_warp32_variant)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,6 +169,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
+    if args.variant is not None:
+        L.ks_debug_warp32_variant(args.variant)
 
     # ---- inputs: this rank's 4096 seeds, replicated into `sets` perturbed copies (distinct memory, same statistics) ----
     base = make_seeds(rank * BATCH, BATCH)

@@ -36,6 +36,8 @@ const char* ks_last_error(void);
 
 /* test hook: route 32x32 through the generic-size kernel instead of the register-resident one (cross-check). */
 void ks_debug_force_generic(int on);
+/* tuning hook: 0 = 7 warps/SM with the stage-1 vector in an L2 scratch slot, 1 = 4 warps/SM, everything in smem. */
+void ks_debug_warp32_variant(int smem_stash);
 
 /* rows*cols of the modes basis for (cls, n, m); 0 if the shape is not supported. */
 int ks_mode_size(int cls, int n, int m);
@@ -70,6 +72,18 @@ int ks_costgrad(int cls, int n, int m, int batch, const double* modes, const dou
 int ks_precondition(int cls, int n, int m, int batch, const double* state_in, const double* gparams_in,
                     const double* params, uint32_t cmask, double pexp_t, double pexp_x, double* state_out,
                     double* gparams_out, void* stream);
+
+/* hunt(..., 'adj'): _adjoint_descent (optimize.py:367-509) with _process_correction (:2115-2239) for a whole batch.
+ * modes/params are updated in place.  Per-orbit outputs: status (-1 has-not-failed, 0 min step, 2 maxiter,
+ * 3 insufficient decrease -- hunt()'s final promotion -1 -> 1 is left to the caller, optimize.py:351-358), nit,
+ * cost = 1/2|F|^2 at the returned orbit, final step size.  Unlike the evaluation calls this one SYNCHRONISES the
+ * stream every `check_every` passes (<= 0: 64) to stop as soon as every orbit has left the loop; `passes_out`
+ * (host int, may be NULL) receives the number of batched costgrad launches.  Workspace: see the _workspace_bytes. */
+size_t ks_adjoint_descent_workspace_bytes(int cls, int n, int m, int batch);
+int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* params, uint32_t cmask, double tol,
+                       double ftol, int maxiter, double min_step, int preconditioning, double step_size,
+                       int32_t* status_out, int32_t* nit_out, double* cost_out, double* step_out, int check_every,
+                       int* passes_out, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

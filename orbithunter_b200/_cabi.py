@@ -6,6 +6,7 @@ _SIG = {
     "ks_b200_abi_version": (C.c_int, []),
     "ks_last_error": (C.c_char_p, []),
     "ks_debug_force_generic": (None, [C.c_int]),
+    "ks_debug_warp32_variant": (None, [C.c_int]),
     "ks_mode_size": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "ks_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ks_transform": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
@@ -16,6 +17,10 @@ _SIG = {
                               C.c_size_t, _P]),
     "ks_precondition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_uint32, C.c_double, C.c_double, _P, _P,
                                   _P]),
+    "ks_adjoint_descent_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ks_adjoint_descent": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_uint32, C.c_double, C.c_double, C.c_int,
+                                     C.c_double, C.c_int, C.c_double, _P, _P, _P, _P, C.c_int, C.POINTER(C.c_int), _P,
+                                     C.c_size_t, _P]),
 }
 
 EXPORTS = tuple(_SIG)

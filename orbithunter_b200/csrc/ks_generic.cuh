@@ -40,7 +40,8 @@ struct GenArgs {
 
 KS_HD size_t slot_doubles(int n, int m, int cols) {
   const size_t k = m / 2 - 1;
-  return 2 * k * n + (size_t)n * m + (size_t)(n - 1) * cols;  // XC (complex) + FU + TU
+  const size_t d = 2 * k * n + (size_t)n * m + (size_t)(n - 1) * cols;  // XC (complex) + FU + TU
+  return (d + 31) & ~(size_t)31;  // keep every slot 256-byte aligned (XC is accessed as double2)
 }
 KS_HD size_t smem_bytes(int n, int m) {
   const int nmax = n > m ? n : m;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
   __syncthreads();
   double* slot = a.scratch + (size_t)blockIdx.x * ga.slot_doubles;
   double2* XC = reinterpret_cast<double2*>(slot);
-  double* FU = slot + 2 * (size_t)g.k * g.n;
+  double* FU = slot + 2 * (size_t)g.k * g.n;  // even offset: stays 16-byte aligned
   double* TU = FU + (size_t)g.n * g.m;
   const int n2 = g.n / 2;
   const bool fix_t = a.cmask & KS_FIX_T, fix_x = a.cmask & KS_FIX_X, fix_s = (a.cmask & KS_FIX_S) || !REL;

@@ -25,9 +25,19 @@
 namespace ksw32 {
 using ks::static_for;
 
-constexpr int kWarpSmemDoubles = 2 * 480 * 2 + 2 * 1024;  // XB + field stash = 3968 doubles = 31744 B
-constexpr int kWarpsPerCta = 7;
-constexpr int kSmemBytes = kWarpsPerCta * kWarpSmemDoubles * 8;
+// Two build variants of the kernel (template parameter TS = "tuple stash in shared memory"):
+//   TS = false: XB + field stash per warp (31.7 KB) -> 7 warps / SM; the stage-1 state vector (F) round-trips
+//               through an L2-resident global scratch slot and the u modes are re-read from global in phase C.
+//   TS = true : + a lane-private tuple stash (16 KB) holding u's tuples from phase A to C and F from C to E
+//               -> 4 warps / SM, but no global/L2 round trips inside an evaluation.
+constexpr int kXbDoubles = 2 * 480 * 2, kSuDoubles = 2 * 1024, kTsDoubles = 2 * 1024;
+template <bool TS>
+struct Cfg {
+  static constexpr int warp_smem_doubles = kXbDoubles + kSuDoubles + (TS ? kTsDoubles : 0);
+  static constexpr int warps_per_cta = TS ? 4 : 7;
+  static constexpr int smem_bytes = warps_per_cta * warp_smem_doubles * 8;
+};
+constexpr int kMaxWarpsPerCta = 7;
 
 template <int CLS>
 struct Lay {
@@ -122,6 +132,18 @@ KS_DEVI Tup spec_to_tup(const double (&yr)[32], const double (&yi)[32]) {
   return t;
 }
 
+// lane-private tuple stash: slot (J, half) of this lane lives at ts[(2*J + half) * 32 + lane]  (conflict-free LDS/STS.128)
+template <int J>
+KS_DEVI void ts_store(double2* __restrict__ ts, const Tup& t) {
+  ts[(2 * J) * 32] = make_double2(t.a1, t.a2);
+  ts[(2 * J + 1) * 32] = make_double2(t.b1, t.b2);
+}
+template <int J>
+KS_DEVI Tup ts_load(const double2* __restrict__ ts) {
+  const double2 a = ts[(2 * J) * 32], b = ts[(2 * J + 1) * 32];
+  return Tup{a.x, a.y, b.x, b.y};
+}
+
 // d/dt and d/dx acting on a tuple (reference dt :423-430, dx :499-516; frequency tables :5239-5307)
 KS_DEVI Tup dt_tup(const Tup& t, double w) { return Tup{-w * t.a2, w * t.a1, -w * t.b2, w * t.b1}; }
 KS_DEVI Tup dx_tup(const Tup& t, double q) { return Tup{-q * t.b1, -q * t.b2, q * t.a1, q * t.a2}; }
@@ -181,8 +203,9 @@ KS_DEVI void row_forward_store(double (&zr)[32], double (&zi)[32], double2* __re
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------
-template <int CLS, int OP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32_kernel(const KsEvalArgs a) {
+template <int CLS, int OP, bool TS>
+__global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kernel(const KsEvalArgs a) {
+  constexpr int kWarpSmemDoubles = Cfg<TS>::warp_smem_doubles, kWarpsPerCta = Cfg<TS>::warps_per_cta;
   using L = Lay<CLS>;
   constexpr int NM = L::nm;
   constexpr bool REL = (CLS == KS_RELATIVE);
@@ -193,7 +216,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32_kernel(const K
   const int kk = colact ? l16 : 14;  // wavenumber index k' = k - 1 of this lane in COL phases
   double* wsm = smem + warp * kWarpSmemDoubles;
   double2* xb = reinterpret_cast<double2*>(wsm);
-  double* su = wsm + 1920;
+  double* su = wsm + kXbDoubles;
+  double2* ts = reinterpret_cast<double2*>(wsm + kXbDoubles + kSuDoubles) + lane;  // only dereferenced when TS
   double2* xcol = xb + o * 480 + kk;
   double2* xrow_a = xb + o * 480 + l16 * 15;
   double2* xrow_b = xb + o * 480 + (l16 + 16) * 15;
@@ -225,7 +249,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32_kernel(const K
       double yr[32], yi[32];
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
-        tup_to_spec<J>(load_tup<CLS, J>(Mp), yr, yi);
+        const Tup t = load_tup<CLS, J>(Mp);
+        if constexpr (TS) ts_store<J>(ts, t);
+        tup_to_spec<J>(t, yr, yi);
       });
       col_inverse_store(yr, yi, xcol, colact);
     }
@@ -278,7 +304,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32_kernel(const K
         const double qn = (J == 0 ? ks::kSqrt2 * cN : cN) * q;
         Tup N{-qn * P.b1, -qn * P.b2, qn * P.a1, qn * P.a2};
         project<CLS, J>(N);
-        const Tup Mt = load_tup<CLS, J>(Mp);
+        Tup Mt;
+        if constexpr (TS) Mt = ts_load<J>(ts); else Mt = load_tup<CLS, J>(Mp);
         if constexpr (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) {
           // F = u_t + u_xx + u_xxxx [- (S/T) u_x] + 1/2 (u^2)_x        (:1918-1922, :3052-3057, :1950)
           Tup F;
@@ -295,7 +322,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32_kernel(const K
           }
           project<CLS, J>(F);
           s_ff += dot_tup(F, F);
-          if (st) store_tup<CLS, J>(Fp, F);
+          if constexpr (TS && OP == KS_OP_COSTGRAD) {
+            ts_store<J>(ts, F);
+            if (st && a.f_out) store_tup<CLS, J>(Fp, F);
+          } else {
+            if (st) store_tup<CLS, J>(Fp, F);
+          }
           if constexpr (OP == KS_OP_COSTGRAD) {
             s_mf += dot_tup(Mt, F);
             s_x = fma(w, rot_t(Mt, F), s_x);
@@ -333,7 +365,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32_kernel(const K
           R.b1 += fma(ce, Mt.b1, fma(-cdt, Mt.b2, fma(cdx, Mt.a1, -vx * N.b1)));
           R.b2 += fma(ce, Mt.b2, fma(cdt, Mt.b1, fma(cdx, Mt.a2, -vx * N.b2)));
           project<CLS, J>(R);
-          if (st) store_tup<CLS, J>(Fp, R);
+          if constexpr (TS) ts_store<J>(ts, R); else { if (st) store_tup<CLS, J>(Fp, R); }
           tup_to_spec<J>(V, yr, yi);
         }
       });
@@ -397,12 +429,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32_kernel(const K
         Tup R;
         if constexpr (OP == KS_OP_MATVEC) {
           // + 2 * 1/2 Dx(u v)                                                        (:692)
-          const Tup A0 = load_tup<CLS, J>(Fp);
+          Tup A0;
+          if constexpr (TS) A0 = ts_load<J>(ts); else A0 = load_tup<CLS, J>(Fp);
           const double qp = cp * q;
           R = Tup{fma(-qp, P.b1, A0.a1), fma(-qp, P.b2, A0.a2), fma(qp, P.a1, A0.b1), fma(qp, P.a2, A0.b2)};
         } else {
           // J^T v = -v_t + v_xx + v_xxxx [+ (S/T) v_x] - FFT2(u .* IFFT2(Dx v))       (:2041-2045, :3110-3115, :1977)
-          const Tup V = (OP == KS_OP_COSTGRAD) ? load_tup<CLS, J>(Fp) : load_tup<CLS, J>(Vp);
+          Tup V;
+          if constexpr (OP == KS_OP_COSTGRAD) {
+            if constexpr (TS) V = ts_load<J>(ts); else V = load_tup<CLS, J>(Fp);
+          } else {
+            V = load_tup<CLS, J>(Vp);
+          }
           R.a1 = fma(d, V.a1, fma(w, V.a2, -cp * P.a1));
           R.a2 = fma(d, V.a2, fma(-w, V.a1, -cp * P.a2));
           R.b1 = fma(d, V.b1, fma(w, V.b2, -cp * P.b1));

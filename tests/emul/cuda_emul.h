@@ -18,6 +18,7 @@
 #include <vector>
 
 #define __global__
+#define __shared__ static  /* blocks run one after another, so one static instance emulates per-block shared memory */
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
@@ -42,6 +43,12 @@ static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emul"; }
 template <class F>
 static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+  std::memcpy(d, s, n);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
   std::memset(p, v, n);
   return cudaSuccess;
@@ -98,6 +105,9 @@ static inline double __shfl_sync(unsigned, double v, int src_lane) {
 }
 static inline int __shfl_sync(unsigned m, int v, int src_lane) { return (int)__shfl_sync(m, (double)v, src_lane); }
 using std::pow;
+using std::fmax;
+using std::fabs;
+using std::sqrt;
 static inline double __ldg(const double* p) { return *p; }
 static inline void sincospi(double x, double* s, double* c) {
   const long double a = 3.14159265358979323846264338327950288L * (long double)x;

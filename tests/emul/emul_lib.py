@@ -102,3 +102,21 @@ def costgrad(cls, n, m, modes, params, cmask, precond=False, want_f=True):
     _chk(L, L.ks_costgrad(cls, n, m, B, _p(modes), _p(params), cmask, int(precond), _p(cost), _p(g), _p(gp), _p(F), _p(ws),
                           nb, None))
     return cost, g, gp, F
+
+
+def adjoint_descent(cls, n, m, modes, params, cmask, tol=1e-6, ftol=1e-9, maxiter=10000, min_step=1e-6, precond=False,
+                    step_size=1.0, check_every=16):
+    L = lib()
+    modes = np.array(modes, dtype=float, order="C")
+    params = np.array(params, dtype=float, order="C")
+    B = modes.shape[0]
+    status = np.zeros(B, dtype=np.int32)
+    nit = np.zeros(B, dtype=np.int32)
+    cost = np.zeros(B)
+    step = np.zeros(B)
+    nb = L.ks_adjoint_descent_workspace_bytes(cls, n, m, B)
+    ws = np.zeros(nb // 8 + 1)
+    passes = C.c_int(0)
+    _chk(L, L.ks_adjoint_descent(cls, n, m, B, _p(modes), _p(params), cmask, tol, ftol, maxiter, min_step, int(precond), step_size,
+                                 _p(status), _p(nit), _p(cost), _p(step), check_every, C.byref(passes), _p(ws), nb, None))
+    return modes, params, status, nit, cost, step, passes.value

@@ -1,0 +1,50 @@
+"""CPU: the batched solver drivers (C++ host loops + decision kernels) under the CPU-thread emulation vs the oracle's
+restatement of optimize.py -- same status / nit, cost to 1e-10, for every class, with and without preconditioning."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+import emul_lib as E  # noqa: E402
+from conftest import relerr  # noqa: E402
+from oracle import ks_oracle as ko  # noqa: E402
+
+
+@pytest.mark.parametrize("cid", range(4))
+def test_adjoint_descent_matches_oracle(cid):
+    n = m = 32
+    B = 3
+    M = np.stack([ko.populate_state(44.0, 44.0, n, m, 3 + s, cid) for s in range(B)])
+    p = np.tile([44.0, 44.0, 0.0], (B, 1))
+    cons = ko.default_constraints(cid)
+    cmask = sum(1 << i for i in range(3) if cons[i])
+    for pc, maxiter, tol in ((False, 40, 1e-6), (True, 25, 1e-6), (False, 30, 600.0)):
+        Mo, po, status, nit, cost, step, passes = E.adjoint_descent(cid, n, m, M, p, cmask, tol=tol, maxiter=maxiter, precond=pc)
+        for b in range(B):
+            rm, rp, st = ko.adjoint_descent(M[b], p[b], cid, maxiter=maxiter, tol=tol, preconditioning=pc)
+            assert (int(status[b]), int(nit[b])) == (st["status"], st["nit"]), (cid, pc, b)
+            assert abs(cost[b] - st["cost"]) <= 1e-10 * max(1.0, st["cost"])
+            assert step[b] == st["step_size"]
+            assert relerr(Mo[b], rm) < 1e-10 and np.allclose(po[b], rp, rtol=1e-11)
+        assert passes >= int(nit.max())
+
+
+def test_adjoint_descent_exit_codes():
+    """min-step (0), maxiter (2), insufficient decrease (3), already-converged (-1 with nit 0) per orbit in one batch."""
+    n = m = 32
+    M = np.stack([ko.populate_state(44.0, 44.0, n, m, 3, 0), 1e-9 * ko.populate_state(44.0, 44.0, n, m, 4, 0)])
+    p = np.tile([44.0, 44.0, 0.0], (2, 1))
+    # orbit 1 starts below tol: loop never entered
+    Mo, po, status, nit, cost, step, _ = E.adjoint_descent(0, n, m, M, p, 4, maxiter=5)
+    assert status[1] == -1 and nit[1] == 0 and np.array_equal(Mo[1], M[1]) and status[0] == 2 and nit[0] == 5
+    # huge ftol -> status 3 on the first counted step, orbit unchanged
+    Mo, po, status, nit, cost, step, _ = E.adjoint_descent(0, n, m, M[:1], p[:1], 4, maxiter=50, ftol=0.9)
+    rm, rp, st = ko.adjoint_descent(M[0], p[0], 0, maxiter=50, ftol=0.9)
+    assert status[0] == 3 == st["status"] and nit[0] == st["nit"] and relerr(Mo[0], rm) < 1e-12
+    # min_step just under the first accepted step size -> status 0
+    rm, rp, st = ko.adjoint_descent(M[0], p[0], 0, maxiter=50, min_step=0.2)
+    Mo, po, status, nit, cost, step, _ = E.adjoint_descent(0, n, m, M[:1], p[:1], 4, maxiter=50, min_step=0.2)
+    assert (int(status[0]), int(nit[0])) == (st["status"], st["nit"]) and st["status"] == 0
+    assert relerr(Mo[0], rm) < 1e-12

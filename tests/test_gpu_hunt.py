@@ -1,0 +1,88 @@
+"""GPU (-m gpu): hunt() end-state parity with the reference (tests/golden/ks_hunt.npz, produced by the unmodified
+reference) and with the oracle: identical status and nit, cost to 1e-10, parameters to 1e-9."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import ks_oracle as ko
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _cls(cid):
+    from orbithunter_b200.ks import CLASSES
+    from orbithunter_b200.batch import CLASS_NAMES
+
+    return CLASSES[CLASS_NAMES[cid]]
+
+
+@pytest.mark.parametrize("cid", range(4))
+def test_adj_golden_single_orbit_api(gold_hunt, cid):
+    from orbithunter_b200.optimize import hunt
+
+    g = gold_hunt
+    key = f"hunt/{cid}"
+    o = _cls(cid)(state=g[key + "/modes"], basis="modes", parameters=tuple(g[key + "/params"]))
+    for pc, tag in ((False, "/adj300"), (True, "/adj300_pc")):
+        r = hunt(o, "adj", maxiter=300, preconditioning=pc)
+        status, nit = (int(x) for x in g[key + tag + "/status_nit"])
+        assert (r.status, r.nit) == (status, nit)
+        assert abs(r.costs[-1] - g[key + tag + "/costs"][-1]) < 1e-10
+        assert abs(r.costs[0] - g[key + tag + "/costs"][0]) < 1e-10 * g[key + tag + "/costs"][0]
+        assert relerr(r.orbit.state, g[key + tag + "/state"]) < 1e-9
+        assert np.allclose(r.orbit.parameters, g[key + tag + "/params"], rtol=1e-10)
+        assert r.method == "adj" and r.maxiter == 300 and isinstance(r.message, str)
+
+
+def test_adj_seeds_batched(gold_hunt):
+    """BASELINE config 2 settings on reference seeds 0..7 (1500 steps): per-seed status / nit / cost / (T, L)."""
+    from orbithunter_b200 import BatchedOrbitKS
+    from orbithunter_b200.optimize import hunt
+
+    tab = gold_hunt["hunt/seeds_adj1500"]
+    seeds = tab[:, 0].astype(int)
+    M = np.stack([ko.populate_state(44.0, 33.4, 32, 32, int(s), ko.ORBIT) for s in seeds])
+    p = np.tile([44.0, 33.4, 0.0], (len(seeds), 1))
+    r = hunt(BatchedOrbitKS(M, p, "OrbitKS"), "adj", maxiter=1500)
+    assert np.array_equal(r.status.cpu().numpy(), tab[:, 1].astype(int))
+    assert np.array_equal(r.nit.cpu().numpy(), tab[:, 2].astype(int))
+    assert np.allclose(r.costs[-1].cpu().numpy(), tab[:, 3], rtol=0, atol=1e-8)
+    assert np.allclose(r.orbit.cpu_parameters()[:, :2], tab[:, 4:6], rtol=1e-9)
+
+
+def test_adj_converges_status_1(gold_hunt):
+    """The stored rpo perturbed by 1e-3 randn converges under 'adj' with tol 1e-5 (reference: status 1)."""
+    from orbithunter_b200 import RelativeOrbitKS
+    from orbithunter_b200.optimize import hunt
+
+    g = gold_hunt
+    o = RelativeOrbitKS(state=g["hunt/rpo_adj/modes"], basis="modes", parameters=tuple(g["hunt/rpo_adj/params"]))
+    r = hunt(o, "adj", maxiter=20000, tol=1e-5)
+    status, nit = (int(x) for x in g["hunt/rpo_adj/status_nit"])
+    assert r.status == status == 1
+    assert abs(r.nit - nit) <= max(2, nit // 100)  # thousands of data-dependent steps: allow a 1 % drift in the count
+    assert abs(r.costs[-1] - g["hunt/rpo_adj/costs"][-1]) < 1e-7 and r.costs[-1] <= 1e-5
+    assert np.allclose(r.orbit.parameters, g["hunt/rpo_adj/out_params"], rtol=1e-6)
+
+
+def test_mixed_batch_exit_codes_and_lists():
+    """Per-orbit exit codes inside one batch; per-method list kwargs as in optimize.py:414-424."""
+    from orbithunter_b200 import BatchedOrbitKS
+    from orbithunter_b200.optimize import hunt
+
+    M = np.stack([ko.populate_state(44.0, 44.0, 32, 32, 3, 0), 1e-9 * ko.populate_state(44.0, 44.0, 32, 32, 4, 0),
+                  ko.populate_state(44.0, 44.0, 32, 32, 5, 0)])
+    p = np.tile([44.0, 44.0, 0.0], (3, 1))
+    r = hunt(BatchedOrbitKS(M, p, "OrbitKS"), ("adj", "adj"), maxiter=[20, 10], tol=[1e-6, 1e-7], preconditioning=[False, True])
+    st, nit = r.status.cpu().numpy(), [x.cpu().numpy() for x in r.nit]
+    assert st[1] == 1 and nit[0][1] == 0 and st[0] == 2 and list(nit[0][[0, 2]]) == [20, 20] and list(nit[1][[0, 2]]) == [10, 10]
+    assert r.method == ["adj", "adj"] and len(r.costs) == 4
+    for b in (0, 2):
+        m1, p1, s1 = ko.adjoint_descent(M[b], p[b], 0, maxiter=20)
+        m2, p2, s2 = ko.adjoint_descent(m1, p1, 0, maxiter=10, tol=1e-7, preconditioning=True)
+        assert abs(float(r.costs[-1][b]) - s2["cost"]) < 1e-9 * max(1.0, s2["cost"])
+    with pytest.raises(NotImplementedError):
+        hunt(BatchedOrbitKS(M, p, "OrbitKS"), "nelder-mead")
+    with pytest.raises(TypeError):
+        hunt(BatchedOrbitKS(M, p, "OrbitKS"), "adj", tol="tight")
