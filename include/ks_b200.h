@@ -85,6 +85,21 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
                        int32_t* status_out, int32_t* nit_out, double* cost_out, double* step_out, int check_every,
                        int* passes_out, void* ws, size_t ws_bytes, void* stream);
 
+/* hunt(..., 'gmres' | 'lsqr'): _scipy_sparse_linalg_solver_wrapper (optimize.py:1196-1404) for a whole batch.
+ * method 0 = GMRES on the normal equations A^T A dx = -A^T F (optimize.py:1760-1797; restart / inner_maxiter = restart
+ * cycles / rtol / atol as scipy.sparse.linalg.gmres; preconditioning = OrbitKS.preconditioner as M);
+ * method 1 = LSQR on the rectangular system J dx = -F (optimize.py:1731-1759; inner_maxiter = iter_lim, atol, btol,
+ * conlim as scipy.sparse.linalg.lsqr, damp = 0).  Each outer step takes the full step first and halves while
+ * next_cost > cost and step > min_step, then _process_correction.  modes/params updated in place; status/nit/cost per
+ * orbit as for ks_adjoint_descent.  Synchronises the stream while polling.  counters_out (host, 4 x int64, may be
+ * NULL): operator applications, solver steps, line-search evaluations, outer iterations. */
+size_t ks_newton_krylov_workspace_bytes(int cls, int n, int m, int batch, int method, int restart);
+int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* params, uint32_t cmask, int method,
+                     double tol, double ftol, int maxiter, double min_step, int preconditioning, int restart,
+                     int inner_maxiter, double rtol, double atol, double btol, double conlim, int32_t* status_out,
+                     int32_t* nit_out, double* cost_out, long long* counters_out, int check_every, void* ws,
+                     size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@
 #include "ks_adjoint.cuh"
 #include "ks_common.cuh"
 #include "ks_generic.cuh"
+#include "ks_krylov.cuh"
 #include "ks_warp32.cuh"
 
 namespace {
@@ -367,6 +368,242 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
   }
   if (passes_out) *passes_out = passes;
   return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "adjoint descent launch failed");
+}
+
+// ---- Newton-Krylov driver (reference optimize.py:1196-1404, :1682-1850) -----------------------------------------------
+namespace {
+__global__ void nk_init_kernel(int* status, int* nit, int* live, int* searching, const double* cost, double tol, int batch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch) {
+    status[i] = -1;
+    nit[i] = 0;
+    live[i] = cost[i] > tol ? 1 : 0;  // while cost > tol and status == -1            (:1314)
+    searching[i] = 0;
+  }
+}
+__global__ void count_flags_kernel(const int* flags, int batch, int* counter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch && flags[i]) atomicAdd(counter, 1);
+}
+int n_free(uint32_t cmask) { return 3 - ((cmask & 1) + ((cmask >> 1) & 1) + ((cmask >> 2) & 1)); }
+struct NkLayout {
+  size_t total;
+  size_t off[24];
+};
+// carve sizes shared by the _workspace_bytes query and the driver
+NkLayout nk_layout(int cls, int n, int m, int batch, int method, int restart, uint32_t cmask) {
+  const size_t nm = (size_t)(n - 1) * mode_cols(cls, m);
+  const size_t N = nm + 3;  // upper bound on cdof (3 free parameters)
+  (void)cmask;
+  NkLayout L;
+  size_t p = 0;
+  int k = 0;
+  auto take = [&](size_t bytes) {
+    L.off[k++] = p;
+    p += align256(bytes);
+  };
+  take(ks_workspace_bytes(cls, n, m, batch));                 // 0 eval workspace
+  take(batch * nm * 8);                                       // 1 F / y
+  take(batch * N * 8);                                        // 2 rhs b (cdof or Nm)
+  take(batch * N * 8);                                        // 3 vin
+  take(batch * N * 8);                                        // 4 w
+  take(batch * N * 8);                                        // 5 x
+  take(batch * nm * 8);                                       // 6 trial u
+  take((size_t)batch * 24);                                   // 7 trial params
+  take((size_t)batch * 8);                                    // 8 trial cost
+  take((size_t)batch * 8);                                    // 9 step
+  take((size_t)batch * 4);                                    // 10 live
+  take((size_t)batch * 4);                                    // 11 searching
+  take(256);                                                  // 12 counters
+  take((size_t)batch * 16 * 8);                               // 13 solver scalars
+  take((size_t)batch * 8 * 4);                                // 14 solver ints
+  if (method == 0) {
+    take((size_t)batch * (restart + 1) * N * 8);              // 15 V
+    take((size_t)batch * restart * (restart + 1) * 8);        // 16 H
+    take((size_t)batch * restart * 2 * 8);                    // 17 Givens
+    take((size_t)batch * (restart + 1) * 8);                  // 18 S
+  } else {
+    take(batch * nm * 8);                                     // 15 u
+    take(batch * N * 8);                                      // 16 v
+    take(batch * N * 8);                                      // 17 w vector
+    take(8);                                                  // 18 unused
+  }
+  L.total = p;
+  return L;
+}
+}  // namespace
+
+size_t ks_newton_krylov_workspace_bytes(int cls, int n, int m, int batch, int method, int restart) {
+  if (!shape_ok(cls, n, m) || batch <= 0 || method < 0 || method > 1 || (method == 0 && restart < 1)) return 0;
+  return nk_layout(cls, n, m, batch, method, restart, 0).total;
+}
+
+int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* params, uint32_t cmask, int method,
+                     double tol, double ftol, int maxiter, double min_step, int preconditioning, int restart,
+                     int inner_maxiter, double rtol, double atol, double btol, double conlim, int32_t* status_out,
+                     int32_t* nit_out, double* cost_out, long long* counters_out, int check_every, void* ws,
+                     size_t ws_bytes, void* stream) {
+  if (!shape_ok(cls, n, m)) return fail(KS_ERR_SHAPE, "unsupported class / discretization (need even n, m >= 4)");
+  if (batch < 0 || maxiter < 0 || method < 0 || method > 1) return fail(KS_ERR_ARG, "bad batch / maxiter / method");
+  if (counters_out) counters_out[0] = counters_out[1] = counters_out[2] = counters_out[3] = 0;
+  if (batch == 0) return 0;
+  if (!modes || !params || !status_out || !nit_out || !cost_out) return fail(KS_ERR_ARG, "null array argument");
+  const int nm = (n - 1) * mode_cols(cls, m);
+  const int N = nm + n_free(cmask);
+  if (method == 0) {
+    if (restart < 1) return fail(KS_ERR_ARG, "gmres restart must be >= 1");
+    if (restart > N) restart = N;  // scipy: restart = min(restart, n)
+  }
+  const NkLayout lay = nk_layout(cls, n, m, batch, method, restart, cmask);
+  if (!ws || ws_bytes < lay.total) return fail(KS_ERR_WORKSPACE, "workspace too small (see ks_newton_krylov_workspace_bytes)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  auto at = [&](int k) { return base + lay.off[k]; };
+  void* eval_ws = at(0);
+  const size_t eval_bytes = ks_workspace_bytes(cls, n, m, batch);
+  double* Fy = reinterpret_cast<double*>(at(1));
+  double* rhs = reinterpret_cast<double*>(at(2));
+  double* vin = reinterpret_cast<double*>(at(3));
+  double* wout = reinterpret_cast<double*>(at(4));
+  double* xsol = reinterpret_cast<double*>(at(5));
+  double* tu = reinterpret_cast<double*>(at(6));
+  double* tup = reinterpret_cast<double*>(at(7));
+  double* tcost = reinterpret_cast<double*>(at(8));
+  double* step = reinterpret_cast<double*>(at(9));
+  int* live = reinterpret_cast<int*>(at(10));
+  int* searching = reinterpret_cast<int*>(at(11));
+  int* counters = reinterpret_cast<int*>(at(12));  // [0] solver active, [1] line search active, [2] live orbits
+  if (check_every <= 0) check_every = 8;
+  long long n_ops = 0, n_steps = 0, n_ls = 0, n_outer = 0;
+
+  auto poll = [&](int idx, int& value) -> bool {
+    return cudaMemcpyAsync(&value, counters + idx, 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+           cudaStreamSynchronize(s) == cudaSuccess;
+  };
+  auto eval_eqn = [&](const double* u, const double* up, double* f, double* c) {
+    KsEvalArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.modes = u; a.params = up; a.out_state = f; a.out_cost = c; a.batch = batch;
+    return dispatch<KS_OP_EQN>(cls, n, m, a, eval_ws, eval_bytes, stream);
+  };
+  auto op_matvec = [&](const double* v_cdof, double* y) {  // y = J v, v in cdof layout
+    KsEvalArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.modes = modes; a.params = params; a.vmodes = v_cdof; a.vparams = nullptr; a.out_state = y; a.batch = batch;
+    a.cmask = cmask; a.v_ld = N; a.v_tail = 1;
+    ++n_ops;
+    return dispatch<KS_OP_MATVEC>(cls, n, m, a, eval_ws, eval_bytes, stream);
+  };
+  auto op_rmatvec = [&](const double* y, double* w_cdof) {  // w = J^T y, w in cdof layout
+    KsEvalArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.modes = modes; a.params = params; a.vmodes = y; a.out_state = w_cdof; a.batch = batch;
+    a.cmask = cmask; a.out_ld = N; a.out_tail = 1;
+    ++n_ops;
+    return dispatch<KS_OP_RMATVEC>(cls, n, m, a, eval_ws, eval_bytes, stream);
+  };
+
+  // initial cost and loop mask
+  int rc = eval_eqn(modes, params, Fy, cost_out);
+  if (rc != 0) return rc;
+  KS_LAUNCH(nk_init_kernel, (batch + 255) / 256, 256, 0, s, status_out, nit_out, live, searching, cost_out, tol, batch);
+
+  for (int outer = 0; outer <= maxiter; ++outer) {
+    cudaMemsetAsync(counters, 0, 16, s);
+    KS_LAUNCH(count_flags_kernel, (batch + 255) / 256, 256, 0, s, live, batch, counters + 2);
+    int n_live = 0;
+    if (!poll(2, n_live)) return fail(KS_ERR_LAUNCH, "newton-krylov: device error while polling");
+    if (n_live == 0) break;
+    ++n_outer;
+    // right-hand side: -F  (and A^T(-F) for the normal equations)
+    if ((rc = eval_eqn(modes, params, Fy, nullptr)) != 0) return rc;
+    if (method == 0) {
+      KS_LAUNCH(kskry::negate_kernel, 296, 256, 0, s, Fy, Fy, (size_t)batch * nm);
+      if ((rc = op_rmatvec(Fy, rhs)) != 0) return rc;
+      kskry::GmresState g;
+      g.V = reinterpret_cast<double*>(at(15)); g.H = reinterpret_cast<double*>(at(16));
+      g.G = reinterpret_cast<double*>(at(17)); g.S = reinterpret_cast<double*>(at(18));
+      g.x = xsol; g.b = rhs; g.vin = vin; g.w = wout;
+      g.sc = reinterpret_cast<double*>(at(13)); g.ic = reinterpret_cast<int*>(at(14));
+      g.params = params; g.live = live; g.n_active = counters;
+      g.B = batch; g.N = N; g.R = restart; g.maxiter = inner_maxiter; g.n = n; g.m = m; g.cols = mode_cols(cls, m);
+      g.precond = preconditioning; g.cmask = cmask; g.rtol = rtol; g.atol_in = atol;
+      KS_LAUNCH(kskry::gmres_start_kernel, batch, kskry::kThreads, 0, s, g);
+      const long max_steps = (long)inner_maxiter * (restart + 1) + 2;
+      for (long st = 0; st < max_steps; ++st) {
+        if (st % check_every == 0) {
+          int active = 0;
+          if (!poll(0, active)) return fail(KS_ERR_LAUNCH, "newton-krylov: device error while polling");
+          if (active == 0) break;
+        }
+        if ((rc = op_matvec(vin, Fy)) != 0) return rc;
+        if ((rc = op_rmatvec(Fy, wout)) != 0) return rc;
+        cudaMemsetAsync(counters, 0, 4, s);
+        KS_LAUNCH(kskry::gmres_step_kernel, batch, kskry::kThreads, 0, s, g);
+        ++n_steps;
+      }
+    } else {
+      KS_LAUNCH(kskry::negate_kernel, 296, 256, 0, s, Fy, rhs, (size_t)batch * nm);
+      kskry::LsqrState g;
+      g.u = reinterpret_cast<double*>(at(15)); g.v = reinterpret_cast<double*>(at(16));
+      g.wv = reinterpret_cast<double*>(at(17)); g.x = xsol; g.b = rhs; g.vin = vin; g.w = wout;
+      g.sc = reinterpret_cast<double*>(at(13)); g.ic = reinterpret_cast<int*>(at(14));
+      g.live = live; g.n_active = counters;
+      g.B = batch; g.M = nm; g.N = N; g.ld = N; g.iter_lim = inner_maxiter; g.atol = atol; g.btol = btol; g.conlim = conlim;
+      KS_LAUNCH(kskry::lsqr_start_kernel, batch, kskry::kThreads, 0, s, g);
+      const long max_steps = 2L * inner_maxiter + 2;
+      for (long st = 0; st < max_steps; ++st) {
+        if (st % check_every == 0) {
+          int active = 0;
+          if (!poll(0, active)) return fail(KS_ERR_LAUNCH, "newton-krylov: device error while polling");
+          if (active == 0) break;
+        }
+        // steps alternate: A^T u (even), A v (odd); vin / wout are strided by N in both cases
+        if (st % 2 == 0) {
+          KsEvalArgs a;
+          std::memset(&a, 0, sizeof(a));
+          a.modes = modes; a.params = params; a.vmodes = vin; a.out_state = wout; a.batch = batch; a.cmask = cmask;
+          a.v_ld = N; a.out_ld = N; a.out_tail = 1;
+          ++n_ops;
+          rc = dispatch<KS_OP_RMATVEC>(cls, n, m, a, eval_ws, eval_bytes, stream);
+        } else {
+          KsEvalArgs a;
+          std::memset(&a, 0, sizeof(a));
+          a.modes = modes; a.params = params; a.vmodes = vin; a.out_state = wout; a.batch = batch; a.cmask = cmask;
+          a.v_ld = N; a.v_tail = 1; a.out_ld = N;
+          ++n_ops;
+          rc = dispatch<KS_OP_MATVEC>(cls, n, m, a, eval_ws, eval_bytes, stream);
+        }
+        if (rc != 0) return rc;
+        cudaMemsetAsync(counters, 0, 4, s);
+        KS_LAUNCH(kskry::lsqr_step_kernel, batch, kskry::kThreads, 0, s, g);
+        ++n_steps;
+      }
+    }
+    // line search on u + step * dx                                                       (:1373-1399)
+    kskry::NewtonState ns;
+    ns.u = modes; ns.up = params; ns.dx = xsol; ns.tu = tu; ns.tup = tup; ns.tcost = tcost; ns.cost = cost_out;
+    ns.step = step; ns.status = status_out; ns.nit = nit_out; ns.live = live; ns.searching = searching;
+    ns.n_searching = counters + 1; ns.B = batch; ns.nm = nm; ns.N = N; ns.maxiter = maxiter; ns.cmask = cmask;
+    ns.tol = tol; ns.ftol = ftol; ns.min_step = min_step;
+    ns.mode = 0;
+    cudaMemsetAsync(counters + 1, 0, 4, s);
+    KS_LAUNCH(kskry::newton_step_kernel, batch, kskry::kThreads, 0, s, ns);
+    ns.mode = 1;
+    for (int ls = 0; ls < 1200; ++ls) {
+      if ((rc = eval_eqn(tu, tup, Fy, tcost)) != 0) return rc;
+      cudaMemsetAsync(counters + 1, 0, 4, s);
+      KS_LAUNCH(kskry::newton_step_kernel, batch, kskry::kThreads, 0, s, ns);
+      ++n_ls;
+      int still = 0;
+      if (!poll(1, still)) return fail(KS_ERR_LAUNCH, "newton-krylov: device error while polling");
+      if (still == 0) break;
+    }
+  }
+  if (counters_out) {
+    counters_out[0] = n_ops; counters_out[1] = n_steps; counters_out[2] = n_ls; counters_out[3] = n_outer;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "newton-krylov launch failed");
 }
 
 }  // extern "C"

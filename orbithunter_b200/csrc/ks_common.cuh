@@ -25,7 +25,22 @@ struct KsEvalArgs {
   int batch;
   unsigned cmask;
   int precond;            // costgrad: apply the reference's diagonal preconditioner (ks/orbits.py:1034-1089)
+  // cdof-layout vectors for the Krylov drivers (core.py:1617-1643): leading dimensions in doubles (0 = Nm) and
+  // whether the free parameters ride at the tail of the vector ([state.ravel(), free params in label order])
+  int v_ld, out_ld;
+  int v_tail;             // matvec: read (dT, dL, dS) from vmodes[b*v_ld + Nm + slot] instead of vparams
+  int out_tail;           // rmatvec/costgrad: write free parameter components to out_state[b*out_ld + Nm + slot]
 };
+
+namespace ks {
+// slot of parameter i (0 t, 1 x, 2 s) among the free ones, or -1 if it is constrained
+KS_HD int free_slot(unsigned cmask, int i) {
+  if ((cmask >> i) & 1u) return -1;
+  int slot = 0;
+  for (int k = 0; k < i; ++k) slot += ((cmask >> k) & 1u) ? 0 : 1;
+  return slot;
+}
+}  // namespace ks
 
 namespace ks {
 template <int B, int E, class F>

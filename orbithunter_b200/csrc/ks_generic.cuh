@@ -325,8 +325,9 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
       continue;
     } else {
       const double* Mo = a.modes + (size_t)orbit * g.nm;
-      const double* Vo = (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) ? a.vmodes + (size_t)orbit * g.nm : nullptr;
-      double* Oo = a.out_state + (size_t)orbit * g.nm;
+      const int v_ld = a.v_ld ? a.v_ld : g.nm, out_ld = a.out_ld ? a.out_ld : g.nm;
+      const double* Vo = (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) ? a.vmodes + (size_t)orbit * v_ld : nullptr;
+      double* Oo = a.out_state + (size_t)orbit * out_ld;
       double* Fo = (OP == KS_OP_COSTGRAD) ? (a.f_out ? a.f_out + (size_t)orbit * g.nm : TU) : Oo;
       const double T = a.params[orbit * 3 + 0], Lx = a.params[orbit * 3 + 1], S = a.params[orbit * 3 + 2];
       const double wbase = -1.0 * (ks::kTwoPi * g.n / T), qbase = ks::kTwoPi * g.m / Lx;
@@ -334,9 +335,14 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
       const bool need_nuu = (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) || !fix_x;
       double vt = 0.0, vx = 0.0, vs = 0.0;
       if constexpr (OP == KS_OP_MATVEC) {
-        vt = fix_t ? 0.0 : a.vparams[orbit * 3 + 0] * (-1.0 / T);
-        vx = fix_x ? 0.0 : a.vparams[orbit * 3 + 1] * (1.0 / Lx);
-        vs = fix_s ? 0.0 : a.vparams[orbit * 3 + 2] * (-1.0 / T);
+        double v3[3];
+        for (int i = 0; i < 3; ++i) {
+          const int slot = ks::free_slot(a.cmask, i);
+          v3[i] = a.v_tail ? (slot < 0 ? 0.0 : Vo[g.nm + slot]) : a.vparams[orbit * 3 + i];
+        }
+        vt = fix_t ? 0.0 : v3[0] * (-1.0 / T);
+        vx = fix_x ? 0.0 : v3[1] * (1.0 / Lx);
+        vs = fix_s ? 0.0 : v3[2] * (-1.0 / T);
       }
       // A: u modes -> XC
       pass_col_inverse<CLS>(g, [&](int j, int kp) { return gload<CLS>(Mo, j, kp, g); }, XC, line, tmp, tw_n);
@@ -436,15 +442,23 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
             t3 += red[wq * 8 + 3];
           }
           if ((OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) && a.out_cost) a.out_cost[orbit] = 0.5 * t0;
-          if ((OP == KS_OP_COSTGRAD || OP == KS_OP_RMATVEC) && a.out_params) {
+          if ((OP == KS_OP_COSTGRAD || OP == KS_OP_RMATVEC) && (a.out_params || a.out_tail)) {
             double gt = fix_t ? 0.0 : (-1.0 / T) * t2, gx = fix_x ? 0.0 : (1.0 / Lx) * t1, gs = fix_s ? 0.0 : (-1.0 / T) * t3;
             if (OP == KS_OP_COSTGRAD && a.precond) {
               if (!fix_t) gt *= 1.0 / T;
               if (!fix_x) gx *= 1.0 / ((Lx * Lx) * (Lx * Lx));
             }
-            a.out_params[orbit * 3 + 0] = gt;
-            a.out_params[orbit * 3 + 1] = gx;
-            a.out_params[orbit * 3 + 2] = gs;
+            if (a.out_tail) {
+              const double g3[3] = {gt, gx, gs};
+              for (int i = 0; i < 3; ++i) {
+                const int slot = ks::free_slot(a.cmask, i);
+                if (slot >= 0) Oo[g.nm + slot] = g3[i];
+              }
+            } else {
+              a.out_params[orbit * 3 + 0] = gt;
+              a.out_params[orbit * 3 + 1] = gx;
+              a.out_params[orbit * 3 + 2] = gs;
+            }
           }
         }
       }

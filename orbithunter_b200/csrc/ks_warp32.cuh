@@ -276,12 +276,13 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
     }
     __syncwarp();
     // ---------------- phase C (COL): tuple stage 1, then second inverse transform ----------------
+    const int v_ld = a.v_ld ? a.v_ld : NM, out_ld = a.out_ld ? a.out_ld : NM;
     double* Fp = nullptr;  // where the stage-1 state vector (F or partial matvec) lives until stage 2
-    if constexpr (OP == KS_OP_EQN) Fp = a.out_state + (size_t)ob * NM + kk;
+    if constexpr (OP == KS_OP_EQN) Fp = a.out_state + (size_t)ob * out_ld + kk;
     if constexpr (OP == KS_OP_COSTGRAD)
       Fp = (a.f_out ? a.f_out + (size_t)ob * NM : a.scratch + (size_t)(2 * gw + o) * NM) + kk;
-    if constexpr (OP == KS_OP_MATVEC) Fp = a.out_state + (size_t)ob * NM + kk;
-    const double* Vp = (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) ? a.vmodes + (size_t)ob * NM + kk : nullptr;
+    if constexpr (OP == KS_OP_MATVEC) Fp = a.out_state + (size_t)ob * out_ld + kk;
+    const double* Vp = (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) ? a.vmodes + (size_t)ob * v_ld + kk : nullptr;
     {
       double yr[32], yi[32];
       if (need_nuu) {
@@ -293,9 +294,15 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
       double s_ff = 0.0, s_mf = 0.0, s_x = 0.0, s_d = 0.0, s_nv = 0.0;
       double vt = 0.0, vx = 0.0, vs = 0.0;
       if constexpr (OP == KS_OP_MATVEC) {
-        vt = fix_t ? 0.0 : a.vparams[ob * 3 + 0] * (-1.0 / T);
-        vx = fix_x ? 0.0 : a.vparams[ob * 3 + 1] * (1.0 / Lx);
-        vs = fix_s ? 0.0 : a.vparams[ob * 3 + 2] * (-1.0 / T);
+        double v3[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int slot = ks::free_slot(a.cmask, i);
+          v3[i] = a.v_tail ? (slot < 0 ? 0.0 : a.vmodes[(size_t)ob * v_ld + NM + slot]) : a.vparams[ob * 3 + i];
+        }
+        vt = fix_t ? 0.0 : v3[0] * (-1.0 / T);
+        vx = fix_x ? 0.0 : v3[1] * (1.0 / Lx);
+        vs = fix_s ? 0.0 : v3[2] * (-1.0 / T);
       }
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
@@ -389,15 +396,24 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
         px = half_reduce(px);
         pt = half_reduce(pt);
         if constexpr (REL) ps = half_reduce(ps);
-        if (valid && l16 == 0 && a.out_params) {
+        if (valid && l16 == 0 && (a.out_params || a.out_tail)) {
           double gt = fix_t ? 0.0 : (-1.0 / T) * pt, gx = fix_x ? 0.0 : (1.0 / Lx) * px, gs = fix_s ? 0.0 : (-1.0 / T) * ps;
           if (OP == KS_OP_COSTGRAD && a.precond) {  // t <- t / T, x <- x / L^4              (:1069-1078)
             if (!fix_t) gt *= 1.0 / T;
             if (!fix_x) gx *= 1.0 / ((Lx * Lx) * (Lx * Lx));
           }
-          a.out_params[orbit * 3 + 0] = gt;
-          a.out_params[orbit * 3 + 1] = gx;
-          a.out_params[orbit * 3 + 2] = gs;
+          if (a.out_tail) {
+            const double g3[3] = {gt, gx, gs};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int slot = ks::free_slot(a.cmask, i);
+              if (slot >= 0) a.out_state[(size_t)orbit * out_ld + NM + slot] = g3[i];
+            }
+          } else {
+            a.out_params[orbit * 3 + 0] = gt;
+            a.out_params[orbit * 3 + 1] = gx;
+            a.out_params[orbit * 3 + 2] = gs;
+          }
         }
       }
       if constexpr (OP == KS_OP_EQN) continue;
@@ -420,7 +436,7 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
     {
       double yr[32], yi[32];
       col_load_forward(xcol, yr, yi);
-      double* Op = a.out_state + (size_t)ob * NM + kk;
+      double* Op = a.out_state + (size_t)ob * out_ld + kk;
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
         const double w = (J == 0) ? 0.0 : wbase * (J * (1.0 / 32.0));

@@ -1,0 +1,73 @@
+"""Newton-Krylov methods of hunt() on the device: 'gmres', 'lsqr' and the matrix-free 'newton_descent'.
+
+Reference: orbithunter/optimize.py _scipy_sparse_linalg_solver_wrapper :1196-1404 (+ _sparse_linalg_factory :1682-1850)
+and _newton_descent :653-852.  ``scipy_kwargs`` keeps SciPy's names: gmres -> restart, maxiter (restart cycles), rtol,
+atol; lsqr -> atol, btol, conlim, iter_lim (damp must be 0).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from .batch import BatchedOrbitKS, workspace
+
+
+def _pop(value):
+    return value.pop(0) if isinstance(value, list) else value
+
+
+def newton_krylov(orb: BatchedOrbitKS, method="gmres", tol=1e-6, ftol=1e-9, maxiter=10000, min_step=1e-6,
+                  preconditioning=False, scipy_kwargs=None, **kwargs):
+    from .optimize import _check_types
+
+    _check_types(tol, ftol, maxiter, min_step, preconditioning)
+    tol, ftol, maxiter, min_step, preconditioning = (_pop(v) for v in (tol, ftol, maxiter, min_step, preconditioning))
+    if not kwargs.get("backtracking", True):
+        min_step = 1
+    sk = dict(scipy_kwargs or {})
+    orb._need_modes()
+    out = orb.copy()
+    B, dev = out.batch, out.state.device
+    N = out.state.shape[1] * out.state.shape[2] + len(out.free_indices())
+    if method == "gmres":
+        mid, restart = 0, int(sk.pop("restart", 20) or 20)
+        inner = sk.pop("maxiter", None)
+        inner = 10 * N if inner is None else int(inner)
+        rtol, atol, btol, conlim = float(sk.pop("rtol", 1e-5)), float(sk.pop("atol", 0.0)), 0.0, 0.0
+    elif method == "lsqr":
+        mid, restart = 1, 1
+        if sk.pop("damp", 0.0):
+            raise NotImplementedError("lsqr damp != 0 is not provided on the device path")
+        inner = sk.pop("iter_lim", None)
+        inner = 2 * N if inner is None else int(inner)
+        rtol, atol, btol, conlim = 0.0, float(sk.pop("atol", 1e-6)), float(sk.pop("btol", 1e-6)), float(sk.pop("conlim", 1e8))
+        preconditioning = False  # the reference never preconditions lsqr/lsmr (optimize.py:1317-1321)
+    elif method == "newton_descent":
+        # dx = pinv(J) (-F): the minimum-norm least-squares step, which LSQR from x0 = 0 converges to.  Stated
+        # tolerance of the restatement: atol = btol = 1e-13, up to 4 N Golub-Kahan steps, no condition limit.
+        mid, restart, preconditioning = 1, 1, False
+        inner, rtol, atol, btol, conlim = 4 * N, 0.0, 1e-13, 1e-13, 0.0
+    else:
+        raise ValueError(f"Unknown solver {method}")
+    if sk:
+        raise TypeError(f"unsupported scipy_kwargs for {method}: {sorted(sk)}")
+    L = _lib.lib()
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    nit = torch.empty(B, dtype=torch.int32, device=dev)
+    cost = torch.empty(B, dtype=torch.float64, device=dev)
+    initial_cost = orb.cost()
+    nbytes = L.ks_newton_krylov_workspace_bytes(out.cls_id, out.n, out.m, B, mid, restart)
+    ws = workspace(dev, nbytes)
+    counters = (ctypes.c_longlong * 4)()
+    with torch.cuda.device(dev):
+        _lib.check(L.ks_newton_krylov(out.cls_id, out.n, out.m, B, out.state.data_ptr(), out.parameters.data_ptr(), out.cmask, mid,
+                                      float(tol), float(ftol), int(maxiter), float(min_step), int(bool(preconditioning)), restart,
+                                      inner, rtol, atol, btol, conlim, status.data_ptr(), nit.data_ptr(), cost.data_ptr(), counters,
+                                      int(kwargs.get("check_every", 8)), ws.data_ptr(), ws.numel(),
+                                      torch.cuda.current_stream().cuda_stream))
+    stats = {"method": method, "nit": nit, "costs": [initial_cost, cost], "maxiter": maxiter, "tol": tol, "status": status,
+             "operator_applications": counters[0], "solver_steps": counters[1], "line_search_evals": counters[2],
+             "outer_iterations": counters[3]}
+    return out, stats

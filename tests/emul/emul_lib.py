@@ -120,3 +120,20 @@ def adjoint_descent(cls, n, m, modes, params, cmask, tol=1e-6, ftol=1e-9, maxite
     _chk(L, L.ks_adjoint_descent(cls, n, m, B, _p(modes), _p(params), cmask, tol, ftol, maxiter, min_step, int(precond), step_size,
                                  _p(status), _p(nit), _p(cost), _p(step), check_every, C.byref(passes), _p(ws), nb, None))
     return modes, params, status, nit, cost, step, passes.value
+
+
+def newton_krylov(cls, n, m, modes, params, cmask, method, tol=1e-6, ftol=1e-9, maxiter=10000, min_step=1e-6, precond=False,
+                  restart=20, inner=None, rtol=1e-5, atol=0.0, btol=1e-6, conlim=1e8, check_every=4):
+    L = lib()
+    modes = np.array(modes, dtype=float, order="C")
+    params = np.array(params, dtype=float, order="C")
+    B = modes.shape[0]
+    status = np.zeros(B, dtype=np.int32)
+    nit = np.zeros(B, dtype=np.int32)
+    cost = np.zeros(B)
+    nb = L.ks_newton_krylov_workspace_bytes(cls, n, m, B, method, restart)
+    ws = np.zeros(nb // 8 + 1)
+    counters = (C.c_longlong * 4)()
+    _chk(L, L.ks_newton_krylov(cls, n, m, B, _p(modes), _p(params), cmask, method, tol, ftol, maxiter, min_step, int(precond), restart,
+                               inner, rtol, atol, btol, conlim, _p(status), _p(nit), _p(cost), counters, check_every, _p(ws), nb, None))
+    return modes, params, status, nit, cost, list(counters)

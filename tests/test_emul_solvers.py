@@ -48,3 +48,28 @@ def test_adjoint_descent_exit_codes():
     Mo, po, status, nit, cost, step, _ = E.adjoint_descent(0, n, m, M[:1], p[:1], 4, maxiter=50, min_step=0.2)
     assert (int(status[0]), int(nit[0])) == (st["status"], st["nit"]) and st["status"] == 0
     assert relerr(Mo[0], rm) < 1e-12
+
+
+@pytest.mark.parametrize("cid,method,precond", [(1, 0, False), (2, 0, True), (0, 1, False)])
+def test_newton_krylov_matches_scipy_based_oracle(cid, method, precond):
+    """Device GMRES (normal equations, optional diagonal M) / LSQR vs the oracle, which calls SciPy's own solvers as
+    the reference does: same outer status / nit; GMRES trajectories agree to round-off, LSQR to its own sensitivity."""
+    n = m = 16
+    B = 2
+    M = np.stack([ko.populate_state(44.0, 44.0, n, m, 3 + s, cid) for s in range(B)])
+    p = np.tile([44.0, 44.0, 0.3 if cid == 1 else 0.0], (B, 1))
+    cons = ko.default_constraints(cid)
+    cmask = sum(1 << i for i in range(3) if cons[i])
+    if method == 0:
+        kw, okw = dict(restart=10, inner=2, rtol=1e-5), dict(restart=10, maxiter=2)
+    else:
+        kw, okw = dict(inner=30, atol=1e-6), dict(iter_lim=30)
+    Mo, po, status, nit, cost, cnt = E.newton_krylov(cid, n, m, M, p, cmask, method, maxiter=2, precond=precond, **kw)
+    for b in range(B):
+        rm, rp, st = ko.newton_krylov(M[b], p[b], cid, method="gmres" if method == 0 else "lsqr", maxiter=2,
+                                      preconditioning=precond, scipy_kwargs=okw)
+        assert (int(status[b]), int(nit[b])) == (st["status"], st["nit"])
+        tol = 1e-10 if method == 0 else 1e-4
+        assert abs(cost[b] - st["cost"]) <= tol * max(1.0, st["cost"])
+        assert relerr(Mo[b], rm) < tol * 10
+    assert cnt[3] == 2 and cnt[0] > 0

@@ -86,3 +86,75 @@ def test_mixed_batch_exit_codes_and_lists():
         hunt(BatchedOrbitKS(M, p, "OrbitKS"), "nelder-mead")
     with pytest.raises(TypeError):
         hunt(BatchedOrbitKS(M, p, "OrbitKS"), "adj", tol="tight")
+
+
+@pytest.mark.parametrize("cid", range(4))
+def test_newton_krylov_golden(gold_hunt, cid):
+    """hunt('gmres') / hunt('lsqr') end state vs the unmodified reference (which runs SciPy's solvers): identical
+    status and nit; cost to 1e-9 for GMRES.  Krylov iteration histories themselves are unpinned by the reference."""
+    from orbithunter_b200.optimize import hunt
+
+    g = gold_hunt
+    key = f"hunt/{cid}"
+    o = _cls(cid)(state=g[key + "/modes"], basis="modes", parameters=tuple(g[key + "/params"]))
+    r = hunt(o, "gmres", maxiter=3, scipy_kwargs={"restart": 20, "maxiter": 2})
+    status, nit = (int(x) for x in g[key + "/gmres/status_nit"])
+    assert (r.status, r.nit) == (status, nit)
+    assert abs(r.costs[-1] - g[key + "/gmres/costs"][-1]) < 1e-9 * max(1.0, g[key + "/gmres/costs"][-1])
+    assert relerr(r.orbit.state, g[key + "/gmres/state"]) < 1e-8
+    r = hunt(o, "lsqr", maxiter=3, scipy_kwargs={"iter_lim": 50})
+    status, nit = (int(x) for x in g[key + "/lsqr/status_nit"])
+    assert (r.status, r.nit) == (status, nit)
+    assert abs(r.costs[-1] - g[key + "/lsqr/costs"][-1]) < 1e-3 * max(1.0, g[key + "/lsqr/costs"][-1])
+
+
+def test_gmres_converges_status_1(gold_hunt):
+    """Perturbed rpo: hunt('gmres', restart 50, 4 cycles, rtol 1e-8, tol 1e-8) converges in the reference (status 1, 7 its)."""
+    from orbithunter_b200 import RelativeOrbitKS
+    from orbithunter_b200.optimize import hunt
+
+    g = gold_hunt
+    o = RelativeOrbitKS(state=g["hunt/rpo_adj/modes"], basis="modes", parameters=tuple(g["hunt/rpo_adj/params"]))
+    r = hunt(o, "gmres", maxiter=20, tol=1e-8, scipy_kwargs={"restart": 50, "maxiter": 4, "rtol": 1e-8})
+    status, nit = (int(x) for x in g["hunt/rpo_gmres/status_nit"])
+    assert r.status == status == 1 and r.nit == nit
+    assert abs(r.costs[-1] - g["hunt/rpo_gmres/costs"][-1]) < 1e-10
+    assert np.allclose(r.orbit.parameters, g["hunt/rpo_gmres/out_params"], rtol=1e-8)
+
+
+def test_hybrid_adj_then_gmres_batched_64():
+    """BASELINE config 3 shape in miniature: 64x64 symmetry classes, adjoint warm-up then Newton-GMRES, vs the oracle."""
+    from orbithunter_b200 import BatchedOrbitKS
+    from orbithunter_b200.batch import CLASS_NAMES
+    from orbithunter_b200.optimize import hunt
+
+    for cid in (1, 2, 3):
+        M = np.stack([ko.populate_state(60.0, 44.0, 64, 64, 10 + s, cid) for s in range(3)])
+        p = np.tile([60.0, 44.0, 0.0], (3, 1))
+        r = hunt(BatchedOrbitKS(M, p, CLASS_NAMES[cid]), ("adj", "gmres"), maxiter=[60, 2], tol=[1e-6, 1e-10],
+                 scipy_kwargs=[{}, {"restart": 10, "maxiter": 1, "rtol": 1e-6}])
+        for b in range(3):
+            m1, p1, s1 = ko.adjoint_descent(M[b], p[b], cid, maxiter=60)
+            m2, p2, s2 = ko.newton_krylov(m1, p1, cid, method="gmres", maxiter=2, tol=1e-10,
+                                          scipy_kwargs={"restart": 10, "maxiter": 1, "rtol": 1e-6})
+            assert int(r.nit[0][b]) == s1["nit"] and int(r.nit[1][b]) == s2["nit"]
+            assert int(r.status[b]) == ko.hunt_status(s2, s2["cost"], 1e-10)
+            assert abs(float(r.costs[-1][b]) - s2["cost"]) < 1e-8 * max(1.0, s2["cost"])
+
+
+def test_newton_descent_matrix_free():
+    """'newton_descent' restated matrix-free: the step equals pinv(J)(-F) (dense reference path, optimize.py:785-787)."""
+    from orbithunter_b200 import OrbitKS
+    from orbithunter_b200.optimize import hunt
+
+    M = ko.populate_state(44.0, 44.0, 16, 16, 3, 0)
+    o = OrbitKS(state=M, basis="modes", parameters=(44.0, 44.0, 0.0))
+    J = o.jacobian()
+    F = o.eqn().state.ravel()
+    dx = np.linalg.pinv(J) @ (-F)
+    expect = o.increment(o.from_numpy_array(dx))
+    c0, c1 = o.cost(), expect.cost()
+    r = hunt(o, "newton_descent", maxiter=1)
+    assert r.nit == 1
+    if c1 <= c0:  # full step accepted by the reference logic
+        assert relerr(r.orbit.state, expect.state) < 1e-7 and abs(r.costs[-1] - c1) < 1e-7 * max(1.0, c1)
