@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--sets", type=int, default=4, help="distinct input/output sets rotated to exceed L2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hunt", action="store_true")
+    ap.add_argument("--hunt-maxiter", type=int, default=10000)
     ap.add_argument("--variant", type=int, default=None, help="tuning: warp32 kernel variant (ks_debug_warp32_variant)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -276,6 +278,25 @@ def main():
                 "d2h_bytes_per_step": BATCH * (NM + 3 + 1) * 8, "steps": e2e_steps},
         "gpu_launches": args.steps, "clocks": clocks.summary(), "checksum_cost_sum": checksum,
     }
+    if not args.no_hunt:
+        # BASELINE configs[1] proper: hunt('adj') on the same 4096 seeds (reference defaults tol 1e-6, ftol 1e-9, min_step 1e-6)
+        from orbithunter_b200.optimize import hunt
+
+        orb = BatchedOrbitKS(torch.as_tensor(base), torch.as_tensor(params_h), "OrbitKS", "modes")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = hunt(orb, "adj", maxiter=args.hunt_maxiter)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        st = res.status.cpu().numpy()
+        nit_total = int(res.nit.sum().item())
+        line["adjoint_descent"] = {
+            "orbits": BATCH, "maxiter": args.hunt_maxiter, "wall_s": wall, "descent_steps_per_s": nit_total / wall,
+            "status_counts": {str(k): int((st == k).sum()) for k in (-1, 0, 1, 2, 3)},
+            "converged_orbits_per_s": float((st == 1).sum()) / wall,
+            "median_final_cost": float(res.costs[-1].median().item()),
+            "note": "one GPU (rank 0), one fused costgrad launch + one decision kernel per outer pass",
+        }
     if not args.no_cpu_baseline:
         cores = 1
         sample = 256

@@ -73,6 +73,12 @@ int ks_precondition(int cls, int n, int m, int batch, const double* state_in, co
                     const double* params, uint32_t cmask, double pexp_t, double pexp_x, double* state_out,
                     double* gparams_out, void* stream);
 
+/* OrbitKS.dt (ks/orbits.py:379-440; axis 0, `in` in the modes basis) and OrbitKS.dx (:442-524; axis 1, `in` with
+ * [Re|Im] columns, i.e. spatial_modes or full-class modes, or the k columns of SR/Anti modes for even orders),
+ * any non-negative order.  in/out: [batch][rows][cols], out must not alias in. */
+int ks_deriv(int cls, int n, int m, int batch, int axis, int order, int rows, int cols, const double* in,
+             const double* params, double* out, void* stream);
+
 /* hunt(..., 'adj'): _adjoint_descent (optimize.py:367-509) with _process_correction (:2115-2239) for a whole batch.
  * modes/params are updated in place.  Per-orbit outputs: status (-1 has-not-failed, 0 min step, 2 maxiter,
  * 3 insufficient decrease -- hunt()'s final promotion -1 -> 1 is left to the caller, optimize.py:351-358), nit,

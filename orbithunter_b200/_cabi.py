@@ -17,6 +17,7 @@ _SIG = {
                               C.c_size_t, _P]),
     "ks_precondition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_uint32, C.c_double, C.c_double, _P, _P,
                                   _P]),
+    "ks_deriv": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "ks_adjoint_descent_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ks_adjoint_descent": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_uint32, C.c_double, C.c_double, C.c_int,
                                      C.c_double, C.c_int, C.c_double, _P, _P, _P, _P, C.c_int, C.POINTER(C.c_int), _P,

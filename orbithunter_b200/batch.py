@@ -196,6 +196,30 @@ class BatchedOrbitKS:
                                          torch.cuda.current_stream().cuda_stream))
         return self._like(out, gp)
 
+    def _deriv(self, axis, order):
+        out = torch.empty_like(self.state)
+        L = _lib.lib()
+        with torch.cuda.device(self.state.device):
+            _lib.check(L.ks_deriv(self.cls_id, self.n, self.m, self.batch, axis, int(order), self.state.shape[1],
+                                  self.state.shape[2], _ptr(self.state), _ptr(self.parameters), _ptr(out),
+                                  torch.cuda.current_stream().cuda_stream))
+        return self._like(out)
+
+    def dt(self, order=1, return_basis=None):
+        """ks/orbits.py:379-440: spectral time derivative, computed in the modes basis."""
+        back = self.basis if return_basis is None else return_basis
+        return self.transform("modes")._deriv(0, order).transform(back)
+
+    def dx(self, order=1, computation_basis=None, return_basis=None):
+        """ks/orbits.py:442-524 and the SR/Anti overrides :3190-3227, :3583-3619 (odd orders in spatial_modes)."""
+        back = self.basis if return_basis is None else return_basis
+        half = self.cls_id in (2, 3)
+        if computation_basis is None:
+            computation_basis = "spatial_modes" if (half and order % 2) else "modes"
+        if computation_basis not in ("modes", "spatial_modes"):
+            raise ValueError(f"dx(computation_basis={computation_basis}); invalid basis for spectral differentiation. ")
+        return self.transform(computation_basis)._deriv(1, order).transform(back)
+
     def dot(self, other):
         return (self.state.reshape(self.batch, -1) * other.state.reshape(self.batch, -1)).sum(dim=1)
 

@@ -40,7 +40,7 @@ int ilog2_exact(int v) {
   return (1 << l) == v ? l : -1;
 }
 bool g_force_generic = false;  // debug/test switch: route 32x32 through the generic kernel as a cross-check
-bool g_warp32_smem_stash = false;  // which warp32 build variant to launch (see ks_warp32.cuh Cfg)
+bool g_warp32_smem_stash = true;   // which warp32 build variant to launch (see ks_warp32.cuh Cfg)
 bool use_warp32(int n, int m) { return n == 32 && m == 32 && !g_force_generic; }
 int warp32_grid(int batch, int warps_per_cta) {
   const int npairs = (batch + 1) / 2;
@@ -261,6 +261,36 @@ int ks_precondition(int cls, int n, int m, int batch, const double* state_in, co
     KS_LAUNCH(ksg::ks_precondition_kernel, dim3(bx, nb), dim3(256), 0, static_cast<cudaStream_t>(stream), c);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "precondition kernel launch failed");
+}
+
+int ks_deriv(int cls, int n, int m, int batch, int axis, int order, int rows, int cols, const double* in,
+             const double* params, double* out, void* stream) {
+  if (!shape_ok(cls, n, m)) return fail(KS_ERR_SHAPE, "unsupported class / discretization (need even n, m >= 4)");
+  if (batch < 0 || order < 0 || (axis != 0 && axis != 1)) return fail(KS_ERR_ARG, "bad batch / order / axis");
+  if (batch == 0) return 0;
+  if (!in || !params || !out || in == out) return fail(KS_ERR_ARG, "null or aliased array argument");
+  const int k = m / 2 - 1;
+  ksg::DerivArgs a;
+  a.in = in; a.params = params; a.out = out; a.batch = batch; a.rows = rows; a.cols = cols; a.n = n; a.m = m;
+  a.axis = axis; a.order = order;
+  if (axis == 0) {
+    if (rows != n - 1) return fail(KS_ERR_SHAPE, "time derivative needs the modes basis (n-1 rows)");
+    a.half = 0;
+  } else {
+    if (cols == 2 * k) a.half = 0;
+    else if (cols == k && (order % 2 == 0)) a.half = 1;
+    else return fail(KS_ERR_SHAPE, "spatial derivative: need [Re|Im] columns, or k columns with an even order");
+  }
+  const int sz = rows * cols;
+  int bx = (sz + 255) / 256;
+  if (bx > 64) bx = 64;
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    ksg::DerivArgs c = a;
+    const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    c.in += (size_t)b0 * sz; c.out += (size_t)b0 * sz; c.params += (size_t)b0 * 3;
+    KS_LAUNCH(ksg::ks_deriv_kernel, dim3(bx, nb), dim3(256), 0, static_cast<cudaStream_t>(stream), c);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "derivative kernel launch failed");
 }
 
 // ---- adjoint descent driver (reference optimize.py:367-509) ------------------------------------------------------

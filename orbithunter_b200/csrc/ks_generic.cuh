@@ -538,4 +538,53 @@ __global__ void ks_precondition_kernel(const PrecArgs a) {
   }
 }
 
+// OrbitKS.dt (ks/orbits.py:379-440) and OrbitKS.dx (:442-524) as standalone elementwise ops on real-packed arrays.
+//   axis 0 (time): `in` has rows [0 | Re j=1..h | Im j=1..h] (modes basis); out = swap^order( [0, c1 w^p, c2 w^p] * in )
+//   axis 1 (space): `in` has columns [Re k=1..K | Im k=1..K] when half == 0 (spatial_modes, or modes of the full
+//                   classes); when half == 1 it has K columns (SR/Anti modes) and only even orders are defined,
+//                   using the first K table entries (:505-508).
+// (c1, c2) = so2_coefficients(order) (:5213-5236); odd orders swap the real and imaginary blocks (swap_modes :5164).
+struct DerivArgs {
+  const double* in;
+  const double* params;
+  double* out;
+  int batch, rows, cols, n, m, axis, order, half;
+};
+__global__ void ks_deriv_kernel(const DerivArgs a) {
+  const int orbit = blockIdx.y;
+  const int h = a.n / 2 - 1, k = a.m / 2 - 1;
+  const size_t sz = (size_t)a.rows * a.cols;
+  const double T = a.params[orbit * 3 + 0], Lx = a.params[orbit * 3 + 1];
+  const double wbase = -1.0 * (ks::kTwoPi * a.n / T), qbase = ks::kTwoPi * a.m / Lx;
+  const int o4 = a.order & 3;
+  const double c1 = (o4 == 0 || o4 == 1) ? 1.0 : -1.0, c2 = (o4 == 0 || o4 == 3) ? 1.0 : -1.0;
+  const bool odd = a.order & 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)sz; i += gridDim.x * blockDim.x) {
+    const int r = i / a.cols, c = i - r * a.cols;
+    double val;
+    int dst;
+    if (a.axis == 0) {
+      if (r == 0) {
+        val = 0.0;
+        dst = i;
+      } else {
+        const bool imag = r > h;
+        const int j = imag ? r - h : r;
+        const double f = pow(wbase * (j * (1.0 / a.n)), (double)a.order);
+        val = (imag ? c2 : c1) * f * a.in[orbit * sz + i];
+        const int rr = odd ? (imag ? r - h : r + h) : r;
+        dst = rr * a.cols + c;
+      }
+    } else {
+      const bool imag = !a.half && c >= k;
+      const int kp = imag ? c - k : c;
+      const double f = pow(qbase * ((kp + 1) * (1.0 / a.m)), (double)a.order);
+      val = (imag ? c2 : c1) * f * a.in[orbit * sz + i];
+      const int cc = (odd && !a.half) ? (imag ? c - k : c + k) : c;
+      dst = r * a.cols + cc;
+    }
+    a.out[orbit * sz + dst] = val;
+  }
+}
+
 }  // namespace ksg

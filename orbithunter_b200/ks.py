@@ -229,6 +229,26 @@ class OrbitKS:
             return self.state if array else self
         return out if array else self._new(state=out, basis=to)
 
+    # ---- spectral derivatives (ks/orbits.py:379-524; SR/Anti :3190-3227, :3583-3619) ------------------------------------
+    def dt(self, order=1, array=False, **kwargs):
+        if getattr(self, "frame", "comoving") != "comoving":
+            raise ValueError(f"Attempting to compute time derivative of {self} in physical reference frame.")
+        back = kwargs.get("return_basis", self.basis)
+        if array:  # the reference returns the modes-basis array in this case (:432-434)
+            return self._host(self._batched().dt(order, return_basis="modes").state)
+        return self._new(state=self._host(self._batched().dt(order, return_basis=back).state), basis=back)
+
+    def dx(self, **kwargs):
+        order, array = kwargs.get("order", 1), kwargs.get("array", False)
+        half = self._cls_id() in (2, 3)
+        comp = kwargs.get("computation_basis", "spatial_modes" if (half and order % 2) else "modes")
+        if half and order % 2:
+            comp = "spatial_modes"
+        back = kwargs.get("return_basis", self.basis)
+        if array:  # array=True returns the derivative in the computation basis (:518-519)
+            return self._host(self._batched().dx(order, comp, return_basis=comp).state)
+        return self._new(state=self._host(self._batched().dx(order, comp, return_basis=back).state), basis=back)
+
     # ---- governing equation and its linearisations ------------------------------------------------------------------
     def eqn(self, **kwargs):
         assert self.basis == "modes", "Convert to spatiotemporal Fourier mode basis before computing K-S equation DAEs."
@@ -272,6 +292,22 @@ class OrbitKS:
         ref = torch.tensor([[float(T), float(L), 0.0]], dtype=torch.float64, device="cuda")
         r = self._batched(basis="modes").precondition(ref, kwargs.get("pexp", (1, 4)))
         return self._new(state=self._host(r.state), basis="modes", parameters=tuple(float(x) for x in self._host(r.parameters)))
+
+    def preconditioner(self, **kwargs):
+        """Diagonal preconditioner as a SciPy LinearOperator (ks/orbits.py:1091-1141); the diagonal comes from the device."""
+        from scipy.sparse.linalg import LinearOperator
+
+        ones = self._new(state=np.ones(self.shape), parameters=(1.0, 1.0, 1.0), basis="modes")
+        mult = ones.precondition(**{"pmult": self.preconditioning_parameters(), **kwargs})
+        diag = mult.cdof().reshape(-1, 1)
+
+        def mv(v):
+            return v * diag.reshape(v.shape)
+
+        def mm(V):
+            return diag.reshape(-1, 1) * V
+
+        return LinearOperator(shape=(diag.size, diag.size), matvec=mv, rmatvec=mv, matmat=mm, rmatmat=mm)
 
     def jacobian(self, **kwargs):
         """Dense (Nm x cdof) Jacobian (ks/orbits.py:557-657): one batched matvec over the identity, on the GPU."""

@@ -1,0 +1,69 @@
+"""Multi-GPU orbit-hunting sweep: independent seeds sharded over ranks, one result gather at the end.
+
+The reference has no distributed code; orbits are independent, so the only multi-GPU strategy is
+a contiguous split of the seed range (one process per GPU, torchrun) and a final gather of the per-orbit result
+records over torch.distributed (NCCL on GPUs; gloo in the CPU tests).  No collective runs during the solve.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+RECORD_FIELDS = ("seed", "status", "nit", "cost", "t", "x", "s")
+
+
+def shard_bounds(total, rank, world):
+    """Contiguous shard [lo, hi) of range(total) for `rank`; shard sizes differ by at most one."""
+    base, extra = divmod(int(total), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_records(local: torch.Tensor, dst=0):
+    """Gather (n_local, len(RECORD_FIELDS)) float64 record tensors of unequal length onto `dst` (None elsewhere)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    count = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count)
+    nmax = int(max(int(c) for c in counts))
+    padded = torch.zeros((nmax, local.shape[1]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bufs, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat([b[: int(c)] for b, c in zip(bufs, counts)], dim=0)
+
+
+def hunt_sweep(cls_name, n_seeds, T, L, discretization, methods="adj", chunk=4096, first_seed=0, device=None, **hunt_kwargs):
+    """Hunt seeds [first_seed, first_seed + n_seeds) of class `cls_name`, sharded over the initialised process group.
+
+    Returns on rank 0 a (n_seeds, 7) float64 tensor with columns RECORD_FIELDS, ordered by seed; None on other ranks.
+    Seeds come from the reference's generator (populate(attr='state', seed=i), ks/orbits.py:1738), produced on the host.
+    """
+    from .batch import BatchedOrbitKS
+    from .ks import CLASSES
+    from .optimize import hunt
+
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lo, hi = shard_bounds(n_seeds, rank, world)
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    records = []
+    cls = CLASSES[cls_name]
+    for c0 in range(lo, hi, chunk):
+        seeds = np.arange(first_seed + c0, first_seed + min(c0 + chunk, hi))
+        states = np.stack([cls(parameters=(T, L, 0.0)).populate(attr="state", seed=int(s), discretization=discretization).state
+                           for s in seeds])
+        params = np.tile([float(T), float(L), 0.0], (len(seeds), 1))
+        batch = BatchedOrbitKS(torch.as_tensor(states).to(device), torch.as_tensor(params).to(device), cls_name, "modes")
+        res = hunt(batch, methods, **{k: (v.copy() if hasattr(v, "copy") else v) for k, v in hunt_kwargs.items()})
+        rec = torch.stack([torch.as_tensor(seeds, dtype=torch.float64, device=device), res.status.to(torch.float64),
+                           (res.nit[-1] if isinstance(res.nit, list) else res.nit).to(torch.float64), res.costs[-1],
+                           res.orbit.parameters[:, 0], res.orbit.parameters[:, 1], res.orbit.parameters[:, 2]], dim=1)
+        records.append(rec)
+    local = torch.cat(records, dim=0) if records else torch.zeros((0, len(RECORD_FIELDS)), dtype=torch.float64, device=device)
+    return gather_records(local)

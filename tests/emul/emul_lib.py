@@ -137,3 +137,20 @@ def newton_krylov(cls, n, m, modes, params, cmask, method, tol=1e-6, ftol=1e-9, 
     _chk(L, L.ks_newton_krylov(cls, n, m, B, _p(modes), _p(params), cmask, method, tol, ftol, maxiter, min_step, int(precond), restart,
                                inner, rtol, atol, btol, conlim, _p(status), _p(nit), _p(cost), counters, check_every, _p(ws), nb, None))
     return modes, params, status, nit, cost, list(counters)
+
+
+def deriv(cls, n, m, arr, params, axis, order):
+    L = lib()
+    arr = np.ascontiguousarray(arr, dtype=float)
+    params = np.ascontiguousarray(params, dtype=float)
+    out = np.zeros_like(arr)
+    _chk(L, L.ks_deriv(cls, n, m, arr.shape[0], axis, order, arr.shape[1], arr.shape[2], _p(arr), _p(params), _p(out), None))
+    return out
+
+
+def precondition(cls, n, m, state, gparams, params, cmask, pexp=(1.0, 4.0)):
+    L = lib()
+    state, gparams, params = (np.ascontiguousarray(x, dtype=float) for x in (state, gparams, params))
+    out, gp = np.zeros_like(state), np.zeros_like(gparams)
+    _chk(L, L.ks_precondition(cls, n, m, state.shape[0], _p(state), _p(gparams), _p(params), cmask, pexp[0], pexp[1], _p(out), _p(gp), None))
+    return out, gp

@@ -106,3 +106,20 @@ def test_golden_vectors_through_emulated_kernels(gold_eval):
             _, gs, gp, _ = E.costgrad(cid, 32, 32, M, p, cmask, pc)
             assert relerr(gs[0], g[key + tag]) < 1e-12
             assert np.allclose(gp[0], g[key + tag + "_params"], rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("cid", range(4))
+def test_derivatives_and_precondition(cid):
+    n, m, B = 12, 16, 3
+    M, p, V, vp = _inputs(cid, n, m, B)
+    for order in (1, 2, 3, 4):
+        assert relerr(E.deriv(cid, n, m, M, p, 0, order), ko.dt(M, p[:, 0], order)) < 1e-13
+        sm = ko.inv_time_transform(M, cid)
+        assert relerr(E.deriv(cid, n, m, sm, p, 1, order), ko.dx_spatial(sm, p[:, 1], order)) < 1e-13
+        if cid in (0, 1) or order % 2 == 0:
+            assert relerr(E.deriv(cid, n, m, M, p, 1, order), ko.dx(M, p[:, 1], cid, order)) < 1e-13
+    cons = ko.default_constraints(cid)
+    cmask = sum(1 << i for i in range(3) if cons[i])
+    out, gp = E.precondition(cid, n, m, V, vp, p, cmask)
+    eo, egp = ko.precondition(V, vp, p, n, m, cid, cons)
+    assert relerr(out, eo) < 1e-13 and np.allclose(gp, egp, rtol=1e-13)
