@@ -36,8 +36,10 @@ const char* ks_last_error(void);
 
 /* test hook: route 32x32 through the generic-size kernel instead of the register-resident one (cross-check). */
 void ks_debug_force_generic(int on);
-/* tuning hook: 0 = 7 warps/SM with the stage-1 vector in an L2 scratch slot, 1 = 4 warps/SM, everything in smem. */
-void ks_debug_warp32_variant(int smem_stash);
+/* tuning hook, 32x32 kernel build variant: 0 = 7 warps/SM, stage-1 vector in an L2 scratch slot, plain loads;
+ * 1 = 4 warps/SM, tuples and stage-1 vector stashed in shared memory; 3 = as 0 with every global read staged through
+ * cp.async one transform ahead (u modes of the next pair, u tuples for stage 1, stage-1 vector for stage 2). */
+void ks_debug_warp32_variant(int variant);
 
 /* rows*cols of the modes basis for (cls, n, m); 0 if the shape is not supported. */
 int ks_mode_size(int cls, int n, int m);

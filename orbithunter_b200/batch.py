@@ -40,8 +40,9 @@ _WORKSPACES = {}
 
 
 def workspace(device, nbytes):
-    """Per-device scratch buffer, grown on demand (sized by ks_workspace_bytes); never shrinks."""
-    key = torch.device(device).index or 0
+    """Scratch buffer per (device, current stream), grown on demand (sized by *_workspace_bytes); never shrinks."""
+    dev = torch.device(device)
+    key = (dev.index or 0, torch.cuda.current_stream(dev).cuda_stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)

@@ -40,7 +40,7 @@ int ilog2_exact(int v) {
   return (1 << l) == v ? l : -1;
 }
 bool g_force_generic = false;  // debug/test switch: route 32x32 through the generic kernel as a cross-check
-bool g_warp32_smem_stash = true;   // which warp32 build variant to launch (see ks_warp32.cuh Cfg)
+int g_warp32_variant = 3;  // 0: L2 scratch, 7 warps/SM; 1: smem tuple stash, 4 warps/SM; 3: as 0 with cp.async staging  // which warp32 build variant to launch (see ks_warp32.cuh Cfg)
 bool use_warp32(int n, int m) { return n == 32 && m == 32 && !g_force_generic; }
 int warp32_grid(int batch, int warps_per_cta) {
   const int npairs = (batch + 1) / 2;
@@ -81,9 +81,30 @@ int launch_warp32_v(const KsEvalArgs& a, cudaStream_t s) {
   KS_LAUNCH(kern, warp32_grid(a.batch, Cfg::warps_per_cta), Cfg::warps_per_cta * 32, Cfg::smem_bytes, s, a);
   return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32 kernel launch failed");
 }
+template <int CLS, int OP, bool PC>
+int launch_warp32_as_pc(const KsEvalArgs& a, cudaStream_t s) {
+  using Cfg = ksw32::Cfg<false>;
+  auto kern = ksw32::ks_warp32_kernel<CLS, OP, false, true, PC, false>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes) != cudaSuccess)
+      return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(warp32 async) failed");
+    attr_done = true;
+  }
+  KS_LAUNCH(kern, warp32_grid(a.batch, Cfg::warps_per_cta), Cfg::warps_per_cta * 32, Cfg::smem_bytes, s, a);
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32 async kernel launch failed");
+}
+template <int CLS, int OP>
+int launch_warp32_as(const KsEvalArgs& a, cudaStream_t s) {
+  if constexpr (OP == KS_OP_COSTGRAD) {
+    if (a.precond) return launch_warp32_as_pc<CLS, OP, true>(a, s);
+  }
+  return launch_warp32_as_pc<CLS, OP, false>(a, s);
+}
 template <int CLS, int OP>
 int launch_warp32(const KsEvalArgs& a, cudaStream_t s) {
-  return g_warp32_smem_stash ? launch_warp32_v<CLS, OP, true>(a, s) : launch_warp32_v<CLS, OP, false>(a, s);
+  if (g_warp32_variant == 3) return launch_warp32_as<CLS, OP>(a, s);
+  return g_warp32_variant == 1 ? launch_warp32_v<CLS, OP, true>(a, s) : launch_warp32_v<CLS, OP, false>(a, s);
 }
 template <int CLS, int OP>
 int launch_generic(const ksg::GenArgs& ga, cudaStream_t s) {
@@ -140,7 +161,7 @@ int ks_b200_abi_version(void) { return 1; }
 const char* ks_last_error(void) { return g_err; }
 
 void ks_debug_force_generic(int on) { g_force_generic = on != 0; }
-void ks_debug_warp32_variant(int smem_stash) { g_warp32_smem_stash = smem_stash != 0; }
+void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant == 0 || variant == 1 || variant == 3) ? variant : 3; }
 
 int ks_mode_size(int cls, int n, int m) { return shape_ok(cls, n, m) ? (n - 1) * mode_cols(cls, m) : 0; }
 

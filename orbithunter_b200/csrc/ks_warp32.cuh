@@ -160,6 +160,97 @@ KS_DEVI double half_reduce(double v) {  // sum over the 16 lanes that share an o
   return v;
 }
 
+// ---- asynchronous global -> shared staging (cp.async / LDGSTS): latency of the u-mode and stage-1 reloads is hidden
+// behind a transform instead of being paid tuple by tuple.  Destinations are lane-private, so no barrier is needed.
+KS_DEVI void cp_async8(double* smem_dst, const double* gsrc) {
+#ifdef KS_HOST_EMUL
+  *smem_dst = *gsrc;
+#else
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+KS_DEVI void cp_async_commit() {
+#ifndef KS_HOST_EMUL
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+KS_DEVI void cp_async_wait() {
+#ifndef KS_HOST_EMUL
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+// slot numbering of a lane's 62 staged values: tuple J occupies slots base(J) .. base(J)+3 (J = 0: 2 slots)
+KS_HD constexpr int slot_base(int J) { return J == 0 ? 0 : 4 * J - 2; }
+// own-XB-column staging: slot s lives in component (s & 1) of the double2 xcol[(s >> 1) * 15]
+template <int CLS, int J>
+KS_DEVI void stage_tup_col(const double* __restrict__ p, double2* xcol) {
+  using L = Lay<CLS>;
+  double* d = reinterpret_cast<double*>(xcol + (slot_base(J) >> 1) * 15);  // slot_base is even
+  if constexpr (L::full) {
+    if constexpr (J == 0) {
+      cp_async8(d, p);
+      cp_async8(d + 1, p + 15);
+    } else {
+      cp_async8(d, p + J * 30);
+      cp_async8(d + 1, p + (15 + J) * 30);
+      cp_async8(d + 30, p + J * 30 + 15);
+      cp_async8(d + 31, p + (15 + J) * 30 + 15);
+    }
+  } else {
+    cp_async8(d, p + J * 15);
+    if constexpr (J > 0) cp_async8(d + 1, p + (15 + J) * 15);
+  }
+}
+template <int CLS, int J>
+KS_DEVI Tup unstage_tup_col(const double2* xcol) {
+  using L = Lay<CLS>;
+  const double2 lo = xcol[(slot_base(J) >> 1) * 15];
+  if constexpr (L::full) {
+    if constexpr (J == 0) return Tup{lo.x, 0.0, lo.y, 0.0};
+    const double2 hi = xcol[((slot_base(J) >> 1) + 1) * 15];
+    return Tup{lo.x, lo.y, hi.x, hi.y};
+  } else if constexpr (L::has_a(J)) {
+    return Tup{lo.x, J > 0 ? lo.y : 0.0, 0.0, 0.0};
+  } else {
+    return Tup{0.0, 0.0, lo.x, J > 0 ? lo.y : 0.0};
+  }
+}
+// field-stash staging (the u stash is dead between phase D and the next phase B): slot s at su[s * 32]
+template <int CLS, int J>
+KS_DEVI void stage_tup_su(const double* __restrict__ p, double* su) {
+  using L = Lay<CLS>;
+  double* d = su + slot_base(J) * 32;
+  if constexpr (L::full) {
+    if constexpr (J == 0) {
+      cp_async8(d, p);
+      cp_async8(d + 32, p + 15);
+    } else {
+      cp_async8(d, p + J * 30);
+      cp_async8(d + 32, p + (15 + J) * 30);
+      cp_async8(d + 64, p + J * 30 + 15);
+      cp_async8(d + 96, p + (15 + J) * 30 + 15);
+    }
+  } else {
+    cp_async8(d, p + J * 15);
+    if constexpr (J > 0) cp_async8(d + 32, p + (15 + J) * 15);
+  }
+}
+template <int CLS, int J>
+KS_DEVI Tup unstage_tup_su(const double* su) {
+  using L = Lay<CLS>;
+  const double* d = su + slot_base(J) * 32;
+  if constexpr (L::full) {
+    if constexpr (J == 0) return Tup{d[0], 0.0, d[32], 0.0};
+    return Tup{d[0], d[32], d[64], d[96]};
+  } else if constexpr (L::has_a(J)) {
+    return Tup{d[0], J > 0 ? d[32] : 0.0, 0.0, 0.0};
+  } else {
+    return Tup{0.0, 0.0, d[0], J > 0 ? d[32] : 0.0};
+  }
+}
+
 // ---- phase helpers --------------------------------------------------------------------------------------------
 // COL: inverse time transform of the spectrum in (yr, yi); column k' of the XB tile <- X[t], t = 0..31
 KS_DEVI void col_inverse_store(double (&yr)[32], double (&yi)[32], double2* __restrict__ xcol, bool act) {
@@ -169,13 +260,16 @@ KS_DEVI void col_inverse_store(double (&yr)[32], double (&yi)[32], double2* __re
     for (int t = 0; t < 32; ++t) xcol[t * 15] = make_double2(yr[t], yi[t]);
   }
 }
-KS_DEVI void col_load_forward(const double2* __restrict__ xcol, double (&yr)[32], double (&yi)[32]) {
+KS_DEVI void col_load(const double2* __restrict__ xcol, double (&yr)[32], double (&yi)[32]) {
 #pragma unroll
   for (int t = 0; t < 32; ++t) {
     const double2 v = xcol[t * 15];
     yr[t] = v.x;
     yi[t] = v.y;
   }
+}
+KS_DEVI void col_load_forward(const double2* __restrict__ xcol, double (&yr)[32], double (&yi)[32]) {
+  col_load(xcol, yr, yi);
   ksfft::fft<32, 1>(yr, yi);
 }
 // ROW: rows (ta, tb) of XB -> 64 * (u[ta, x] + i u[tb, x]) by one complex inverse transform (two-for-one)
@@ -203,8 +297,9 @@ KS_DEVI void row_forward_store(double (&zr)[32], double (&zi)[32], double2* __re
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------
-template <int CLS, int OP, bool TS>
+template <int CLS, int OP, bool TS, bool AS = false, bool PC = false, bool PC_RUNTIME = true>
 __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kernel(const KsEvalArgs a) {
+  static_assert(!(TS && AS), "async staging is the no-tuple-stash variant");
   constexpr int kWarpSmemDoubles = Cfg<TS>::warp_smem_doubles, kWarpsPerCta = Cfg<TS>::warps_per_cta;
   using L = Lay<CLS>;
   constexpr int NM = L::nm;
@@ -227,6 +322,14 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
   // does this op need N(u,u) = 1/2 Dx FFT2(u^2)?  eqn/costgrad always; matvec/rmatvec only for the dF/dL column.
   const bool need_nuu = (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) || !fix_x;
 
+  if constexpr (AS) {  // stage the first pair's u modes into the (still unused) field stash
+    if (gw < npairs) {
+      const int ob0 = (2 * gw + o < a.batch) ? 2 * gw + o : a.batch - 1;
+      const double* M0 = a.modes + (size_t)ob0 * NM + kk;
+      static_for<0, 16>([&](auto Jc) { stage_tup_su<CLS, decltype(Jc)::value>(M0, su + lane); });
+    }
+    cp_async_commit();
+  }
 #pragma unroll 1
   for (int pair = gw; pair < npairs; pair += nw) {
     const int orbit = 2 * pair + o;
@@ -247,9 +350,11 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
     // ---------------- phase A (COL): u modes -> X_u ----------------
     {
       double yr[32], yi[32];
+      if constexpr (AS) cp_async_wait<0>();
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
-        const Tup t = load_tup<CLS, J>(Mp);
+        Tup t;
+        if constexpr (AS) t = unstage_tup_su<CLS, J>(su + lane); else t = load_tup<CLS, J>(Mp);
         if constexpr (TS) ts_store<J>(ts, t);
         tup_to_spec<J>(t, yr, yi);
       });
@@ -286,11 +391,18 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
     {
       double yr[32], yi[32];
       if (need_nuu) {
-        col_load_forward(xcol, yr, yi);
+        col_load(xcol, yr, yi);
       } else {
 #pragma unroll
         for (int t = 0; t < 32; ++t) yr[t] = yi[t] = 0.0;
       }
+      if constexpr (AS) {  // the column is in registers now: its slots stage u's tuples while the transform runs
+        // lanes 15/31 mirror a neighbour's column: they must not write into it (their results are discarded anyway)
+        if (colact) static_for<0, 16>([&](auto Jc) { stage_tup_col<CLS, decltype(Jc)::value>(Mp, xcol); });
+        cp_async_commit();
+      }
+      if (need_nuu) ksfft::fft<32, 1>(yr, yi);
+      if constexpr (AS) cp_async_wait<0>();
       double s_ff = 0.0, s_mf = 0.0, s_x = 0.0, s_d = 0.0, s_nv = 0.0;
       double vt = 0.0, vx = 0.0, vs = 0.0;
       if constexpr (OP == KS_OP_MATVEC) {
@@ -312,7 +424,9 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
         Tup N{-qn * P.b1, -qn * P.b2, qn * P.a1, qn * P.a2};
         project<CLS, J>(N);
         Tup Mt;
-        if constexpr (TS) Mt = ts_load<J>(ts); else Mt = load_tup<CLS, J>(Mp);
+        if constexpr (TS) Mt = ts_load<J>(ts);
+        else if constexpr (AS) Mt = unstage_tup_col<CLS, J>(xcol);
+        else Mt = load_tup<CLS, J>(Mp);
         if constexpr (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) {
           // F = u_t + u_xx + u_xxxx [- (S/T) u_x] + 1/2 (u^2)_x        (:1918-1922, :3052-3057, :1950)
           Tup F;
@@ -398,7 +512,7 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
         if constexpr (REL) ps = half_reduce(ps);
         if (valid && l16 == 0 && (a.out_params || a.out_tail)) {
           double gt = fix_t ? 0.0 : (-1.0 / T) * pt, gx = fix_x ? 0.0 : (1.0 / Lx) * px, gs = fix_s ? 0.0 : (-1.0 / T) * ps;
-          if (OP == KS_OP_COSTGRAD && a.precond) {  // t <- t / T, x <- x / L^4              (:1069-1078)
+          if (OP == KS_OP_COSTGRAD && (PC_RUNTIME ? a.precond != 0 : PC)) {  // t <- t / T, x <- x / L^4   (:1069-1078)
             if (!fix_t) gt *= 1.0 / T;
             if (!fix_x) gx *= 1.0 / ((Lx * Lx) * (Lx * Lx));
           }
@@ -416,7 +530,17 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
           }
         }
       }
-      if constexpr (OP == KS_OP_EQN) continue;
+      if constexpr (OP == KS_OP_EQN) {
+        if constexpr (AS) {  // eqn ends here: the next pair's u modes go to the field stash now
+          if (pair + nw < npairs) {
+            const int obn = (2 * (pair + nw) + o < a.batch) ? 2 * (pair + nw) + o : a.batch - 1;
+            const double* Mn = a.modes + (size_t)obn * NM + kk;
+            static_for<0, 16>([&](auto Jc) { stage_tup_su<CLS, decltype(Jc)::value>(Mn, su + lane); });
+          }
+          cp_async_commit();
+        }
+        continue;
+      }
       col_inverse_store(yr, yi, xcol, colact);
     }
     __syncwarp();
@@ -435,7 +559,21 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
     // ---------------- phase E (COL): tuple stage 2 ----------------
     {
       double yr[32], yi[32];
-      col_load_forward(xcol, yr, yi);
+      col_load(xcol, yr, yi);
+      if constexpr (AS) {
+        if constexpr (OP == KS_OP_COSTGRAD || OP == KS_OP_MATVEC) {  // stage-1 vector back from its L2 slot
+          if (colact) static_for<0, 16>([&](auto Jc) { stage_tup_col<CLS, decltype(Jc)::value>(Fp, xcol); });
+        }
+        cp_async_commit();
+        if (pair + nw < npairs) {  // next pair's u modes into the field stash (dead from here to the next phase B)
+          const int obn = (2 * (pair + nw) + o < a.batch) ? 2 * (pair + nw) + o : a.batch - 1;
+          const double* Mn = a.modes + (size_t)obn * NM + kk;
+          static_for<0, 16>([&](auto Jc) { stage_tup_su<CLS, decltype(Jc)::value>(Mn, su + lane); });
+        }
+        cp_async_commit();
+      }
+      ksfft::fft<32, 1>(yr, yi);
+      if constexpr (AS) cp_async_wait<1>();
       double* Op = a.out_state + (size_t)ob * out_ld + kk;
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
@@ -446,14 +584,18 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
         if constexpr (OP == KS_OP_MATVEC) {
           // + 2 * 1/2 Dx(u v)                                                        (:692)
           Tup A0;
-          if constexpr (TS) A0 = ts_load<J>(ts); else A0 = load_tup<CLS, J>(Fp);
+          if constexpr (TS) A0 = ts_load<J>(ts);
+          else if constexpr (AS) A0 = unstage_tup_col<CLS, J>(xcol);
+          else A0 = load_tup<CLS, J>(Fp);
           const double qp = cp * q;
           R = Tup{fma(-qp, P.b1, A0.a1), fma(-qp, P.b2, A0.a2), fma(qp, P.a1, A0.b1), fma(qp, P.a2, A0.b2)};
         } else {
           // J^T v = -v_t + v_xx + v_xxxx [+ (S/T) v_x] - FFT2(u .* IFFT2(Dx v))       (:2041-2045, :3110-3115, :1977)
           Tup V;
           if constexpr (OP == KS_OP_COSTGRAD) {
-            if constexpr (TS) V = ts_load<J>(ts); else V = load_tup<CLS, J>(Fp);
+            if constexpr (TS) V = ts_load<J>(ts);
+            else if constexpr (AS) V = unstage_tup_col<CLS, J>(xcol);
+            else V = load_tup<CLS, J>(Fp);
           } else {
             V = load_tup<CLS, J>(Vp);
           }
@@ -468,7 +610,7 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
             R.b1 = fma(sq, V.a1, R.b1);
             R.b2 = fma(sq, V.a2, R.b2);
           }
-          if (OP == KS_OP_COSTGRAD && a.precond) {  // 1 / (|w_j| + q^2 + q^4)                (:1061-1065)
+          if (OP == KS_OP_COSTGRAD && (PC_RUNTIME ? a.precond != 0 : PC)) {  // 1 / (|w_j| + q^2 + q^4)     (:1061-1065)
             const double pm = 1.0 / ((w < 0 ? -w : w) + q2 + q4);
             R.a1 *= pm; R.a2 *= pm; R.b1 *= pm; R.b2 *= pm;
           }
