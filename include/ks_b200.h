@@ -36,9 +36,8 @@ const char* ks_last_error(void);
 
 /* test hook: route 32x32 through the generic-size kernel instead of the register-resident one (cross-check). */
 void ks_debug_force_generic(int on);
-/* tuning hook, 32x32 kernel build variant: 0 = 7 warps/SM, stage-1 vector in an L2 scratch slot, plain loads;
- * 1 = 4 warps/SM, tuples and stage-1 vector stashed in shared memory; 3 = as 0 with every global read staged through
- * cp.async one transform ahead (u modes of the next pair, u tuples for stage 1, stage-1 vector for stage 2). */
+/* tuning hook, 32x32 kernel build variant: 3 = two orbits per warp, 7 warps/SM, global reads staged with cp.async
+ * (all ops); 4 (default) = one orbit per warp, 8 warps/SM, all state in registers (eqn and costgrad; other ops use 3). */
 void ks_debug_warp32_variant(int variant);
 
 /* rows*cols of the modes basis for (cls, n, m); 0 if the shape is not supported. */

@@ -9,6 +9,7 @@
 #include "ks_generic.cuh"
 #include "ks_krylov.cuh"
 #include "ks_warp32.cuh"
+#include "ks_warp32x1.cuh"
 
 namespace {
 thread_local char g_err[256] = "";
@@ -40,7 +41,7 @@ int ilog2_exact(int v) {
   return (1 << l) == v ? l : -1;
 }
 bool g_force_generic = false;  // debug/test switch: route 32x32 through the generic kernel as a cross-check
-int g_warp32_variant = 3;  // 0: L2 scratch, 7 warps/SM; 1: smem tuple stash, 4 warps/SM; 3: as 0 with cp.async staging  // which warp32 build variant to launch (see ks_warp32.cuh Cfg)
+int g_warp32_variant = 4;  // 3: two orbits per warp, cp.async staging (all ops); 4: one orbit per warp, register-resident (eqn, costgrad)  // which warp32 build variant to launch (see ks_warp32.cuh Cfg)
 bool use_warp32(int n, int m) { return n == 32 && m == 32 && !g_force_generic; }
 int warp32_grid(int batch, int warps_per_cta) {
   const int npairs = (batch + 1) / 2;
@@ -68,19 +69,6 @@ ksg::Geom make_geom(int cls, int n, int m) {
   return g;
 }
 
-template <int CLS, int OP, bool TS>
-int launch_warp32_v(const KsEvalArgs& a, cudaStream_t s) {
-  using Cfg = ksw32::Cfg<TS>;
-  auto kern = ksw32::ks_warp32_kernel<CLS, OP, TS>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes) != cudaSuccess)
-      return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(warp32) failed");
-    attr_done = true;
-  }
-  KS_LAUNCH(kern, warp32_grid(a.batch, Cfg::warps_per_cta), Cfg::warps_per_cta * 32, Cfg::smem_bytes, s, a);
-  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32 kernel launch failed");
-}
 template <int CLS, int OP, bool PC>
 int launch_warp32_as_pc(const KsEvalArgs& a, cudaStream_t s) {
   using Cfg = ksw32::Cfg<false>;
@@ -101,10 +89,31 @@ int launch_warp32_as(const KsEvalArgs& a, cudaStream_t s) {
   }
   return launch_warp32_as_pc<CLS, OP, false>(a, s);
 }
+template <int CLS, int OP, bool PC>
+int launch_warp32x1_pc(const KsEvalArgs& a, cudaStream_t s) {
+  auto kern = ksx1::ks_warp32x1_kernel<CLS, OP, PC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ksx1::kSmemBytes) != cudaSuccess)
+      return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(warp32x1) failed");
+    attr_done = true;
+  }
+  const int ctas = (a.batch + ksx1::kWarpsPerCta - 1) / ksx1::kWarpsPerCta;
+  const int sms = sm_count();
+  KS_LAUNCH(kern, ctas < sms ? ctas : sms, ksx1::kWarpsPerCta * 32, ksx1::kSmemBytes, s, a);
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32x1 kernel launch failed");
+}
 template <int CLS, int OP>
 int launch_warp32(const KsEvalArgs& a, cudaStream_t s) {
-  if (g_warp32_variant == 3) return launch_warp32_as<CLS, OP>(a, s);
-  return g_warp32_variant == 1 ? launch_warp32_v<CLS, OP, true>(a, s) : launch_warp32_v<CLS, OP, false>(a, s);
+  if constexpr (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) {
+    if (g_warp32_variant == 4) {
+      if constexpr (OP == KS_OP_COSTGRAD) {
+        if (a.precond) return launch_warp32x1_pc<CLS, OP, true>(a, s);
+      }
+      return launch_warp32x1_pc<CLS, OP, false>(a, s);
+    }
+  }
+  return launch_warp32_as<CLS, OP>(a, s);
 }
 template <int CLS, int OP>
 int launch_generic(const ksg::GenArgs& ga, cudaStream_t s) {
@@ -161,7 +170,7 @@ int ks_b200_abi_version(void) { return 1; }
 const char* ks_last_error(void) { return g_err; }
 
 void ks_debug_force_generic(int on) { g_force_generic = on != 0; }
-void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant == 0 || variant == 1 || variant == 3) ? variant : 3; }
+void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant == 3 || variant == 4) ? variant : 4; }
 
 int ks_mode_size(int cls, int n, int m) { return shape_ok(cls, n, m) ? (n - 1) * mode_cols(cls, m) : 0; }
 
@@ -171,7 +180,7 @@ size_t ks_workspace_bytes(int cls, int n, int m, int batch) {
   // generic path slots (always available: ks_transform uses it for every shape)
   size_t bytes = (size_t)generic_grid(batch) * ksg::slot_doubles(n, m, cols) * 8;
   if (use_warp32(n, m)) {
-    const size_t w = (size_t)warp32_grid(batch, 4) * ksw32::kMaxWarpsPerCta * 2 * 31 * cols * 8;
+    const size_t w = (size_t)warp32_grid(batch, 7) * ksw32::kMaxWarpsPerCta * 2 * 31 * cols * 8;
     if (w > bytes) bytes = w;
   }
   return bytes;

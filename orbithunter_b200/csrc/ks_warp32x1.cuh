@@ -1,0 +1,360 @@
+// 32x32 eqn / costgrad, "one orbit per warp, state in registers" form (variant 4).
+//
+// Same mathematics and reference citations as ks_warp32.cuh, different work decomposition, chosen after profiling the
+// two-orbits-per-warp kernels (profiles/r01*): those need 128 registers of transform buffer per lane plus 31-47 KB of
+// shared memory per warp, which caps residency at 4-7 warps/SM and forces either L2 round trips or one warp per
+// scheduler.  Here every 1-D transform is a REAL length-32 transform done as a 16-point complex FFT in registers
+// (64 registers of buffer), so the field stash (32 doubles) and the tuple stash (31 doubles) also live in registers,
+// the only shared memory is the 7.5 KB spatial-mode tile, and 8 warps (2 per scheduler) are resident per SM.
+//
+//   ROW phases : lane t owns field row t (32 reals).
+//   COL phases : lane 2c+h owns, for wavenumber c+1, the real sequence A[t] = Re X[t,c] (h = 0) or B[t] = Im X[t,c]
+//                (h = 1); its spectrum is exactly the a-half (a1 + i a2) or b-half (b1 + i b2) of the reference's
+//                tuples, so each lane holds "half tuples" for all 16 time indices.  d/dx (multiplication of X by iq)
+//                is folded into which component of the tile a lane reads or writes, so the two halves never have to be
+//                exchanged except for RelativeOrbitKS' shift terms (warp shuffles).
+// Scalings are those of ks_warp32.cuh: field arrays hold 64 u, forward outputs are doubled, constants cN, cP.
+#pragma once
+#include "ks_warp32.cuh"
+
+namespace ksx1 {
+using ks::static_for;
+using ksfft::cos64;
+using ksfft::sin64;
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kTileDoubles = 32 * 15 * 2;  // XB tile of one orbit: 480 double2
+constexpr int kStageDoubles = 31 * 32;      // cp.async landing zone for the next orbit's half tuples (lane-private slots)
+constexpr int kWarpSmemDoubles = kTileDoubles + kStageDoubles;
+constexpr int kSmemBytes = kWarpsPerCta * kWarpSmemDoubles * 8;
+
+// x[32] real -> c0 = DFT32(x)[0], (cr, ci)[k] = DFT32(x)[k], k = 1..15   (forward sign e^{-i...}, unnormalised).
+// ks_warp32.cuh's convention has the k >= 1 outputs doubled; here that factor (x2 per forward transform, x4 for the two
+// dimensions) is folded into the scale constants applied at the tile loads of the COL phases.
+KS_DEVI void rfft32_fwd(const double (&x)[32], double& c0, double (&cr)[16], double (&ci)[16]) {
+  double yr[17], yi[17];
+  ksfft::rfft_dit<32, 1, 0, 32>(x, yr, yi);
+  c0 = yr[0];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) {
+    cr[k] = yr[k];
+    ci[k] = yi[k];
+  }
+  cr[0] = ci[0] = 0.0;
+}
+
+// h0 real, (hr, hi)[k], k = 1..15 -> x[n] = h0 + sum_k 2 Re(H[k] e^{+2 pi i k n / 32})     (Nyquist term zero)
+KS_DEVI void irfft32(double h0, const double (&hr)[16], const double (&hi)[16], double (&x)[32]) {
+  double gr[16], gi[16];
+  gr[0] = h0;
+  gi[0] = h0;
+  static_for<1, 8>([&](auto Kc) {
+    constexpr int K = decltype(Kc)::value;
+    constexpr double cs = cos64(2 * K), sn = sin64(2 * K);  // i w^K = -sin + i cos
+    const double sr = hr[K] + hr[16 - K], si = hi[K] - hi[16 - K];
+    const double dr = hr[K] - hr[16 - K], di = hi[K] + hi[16 - K];
+    const double tr = -fma(sn, dr, cs * di), ti = fma(cs, dr, -sn * di);
+    gr[K] = sr + tr;
+    gi[K] = si + ti;
+    gr[16 - K] = sr - tr;
+    gi[16 - K] = -(si - ti);
+  });
+  gr[8] = 2.0 * hr[8];
+  gi[8] = -2.0 * hi[8];
+  ksfft::fft<16, -1>(gr, gi);
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    x[2 * m] = gr[m];
+    x[2 * m + 1] = gi[m];
+  }
+}
+
+KS_DEVI double warp_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+template <int CLS, int OP, bool PC>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const KsEvalArgs a) {
+  static_assert(OP == KS_OP_EQN || OP == KS_OP_COSTGRAD, "this form implements eqn and costgrad");
+  constexpr bool FULL = (CLS == KS_ORBIT || CLS == KS_RELATIVE);
+  constexpr bool REL = (CLS == KS_RELATIVE);
+  constexpr int COLS = FULL ? 30 : 15, NM = 31 * COLS;
+  KS_DYN_SMEM(double, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* tile = smem + warp * kWarpSmemDoubles;  // tile[(t * 15 + c) * 2 + component]
+  double* stage = tile + kTileDoubles + lane;     // slot s of this lane at stage[s * 32]
+  const int c = lane >> 1, h = lane & 1;
+  const bool colact = c < 15;
+  const int cc = colact ? c : 14;
+  // which half-tuples exist for this lane: even / odd time index (class projection)
+  const bool presE = FULL || (CLS == KS_ANTISYMMETRIC ? h == 1 : h == 1);
+  const bool presO = FULL || (CLS == KS_ANTISYMMETRIC ? h == 1 : h == 0);
+  const int gw = blockIdx.x * kWarpsPerCta + warp, nw = gridDim.x * kWarpsPerCta;
+  const bool fix_t = a.cmask & KS_FIX_T, fix_x = a.cmask & KS_FIX_X, fix_s = (a.cmask & KS_FIX_S) || !REL;
+  constexpr double cN = 0.5 / (64.0 * 4096.0), cP = 1.0 / (64.0 * 4096.0);
+  // column offset of this lane's half inside a modes row: full classes [Re_x | Im_x], half classes a single block
+  const int coff = (FULL ? h * 15 : 0) + cc;
+
+  // u's half tuples reach the registers through a cp.async landing zone filled one orbit ahead (the first-touch DRAM
+  // latency of the modes was 26 % of the warp-issue samples with plain loads: profiles/r01g_*)
+  auto prefetch = [&](int orb) {
+    if (orb < a.batch) {
+      const double* Mn = a.modes + (size_t)orb * NM + coff;
+      static_for<0, 16>([&](auto Jc) {
+        constexpr int J = decltype(Jc)::value;
+        const bool pres = (J & 1) ? presO : presE;
+        if (pres) {
+          ksw32::cp_async8(stage + (J == 0 ? 0 : 2 * J - 1) * 32, Mn + J * COLS);
+          if constexpr (J > 0) ksw32::cp_async8(stage + (2 * J) * 32, Mn + (15 + J) * COLS);
+        }
+      });
+    }
+    ksw32::cp_async_commit();
+  };
+  prefetch(gw);
+  // parameters of the next orbit are fetched one iteration ahead as well (three plain loads held in registers)
+  double nT = 1.0, nL = 1.0, nS = 0.0;
+  if (gw < a.batch) {
+    nT = a.params[gw * 3 + 0];
+    nL = a.params[gw * 3 + 1];
+    nS = a.params[gw * 3 + 2];
+  }
+#pragma unroll 1
+  for (int orbit = gw; orbit < a.batch; orbit += nw) {
+    const double T = nT, Lx = nL, S = nS;
+    if (orbit + nw < a.batch) {
+      nT = a.params[(orbit + nw) * 3 + 0];
+      nL = a.params[(orbit + nw) * 3 + 1];
+      nS = a.params[(orbit + nw) * 3 + 2];
+    }
+    const double wbase = -1.0 * (ks::kTwoPi * 32.0 / T);
+    const double q = (ks::kTwoPi * 32.0 / Lx) * ((cc + 1) * (1.0 / 32.0));
+    const double q2 = q * q, q4 = q2 * q2, d = q4 - q2;
+    const double sgq = h ? q : -q;  // d/dx: a' = -q b, b' = +q a
+    const double sig = REL ? S / T : 0.0;
+
+    // ---------------- phase A (COL): half tuples of u -> A[t] or B[t] -> tile component h ----------------
+    double m1[16], m2[16];  // half tuples (x1, x2) of u; overwritten by F in stage 1
+    ksw32::cp_async_wait<0>();
+    static_for<0, 16>([&](auto Jc) {
+      constexpr int J = decltype(Jc)::value;
+      const bool pres = (J & 1) ? presO : presE;
+      m1[J] = pres ? stage[(J == 0 ? 0 : 2 * J - 1) * 32] : 0.0;
+      if constexpr (J > 0) m2[J] = pres ? stage[(2 * J) * 32] : 0.0; else m2[J] = 0.0;
+    });
+    prefetch(orbit + nw);
+    {
+      double x[32];
+      double hr[16], hi[16];
+#pragma unroll
+      for (int J = 1; J < 16; ++J) {
+        hr[J] = m1[J];
+        hi[J] = m2[J];
+      }
+      hr[0] = hi[0] = 0.0;
+      irfft32(ks::kSqrt2 * m1[0], hr, hi, x);
+      if (colact) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) tile[(t * 15 + c) * 2 + h] = x[t];
+      }
+    }
+    __syncwarp();
+    // ---------------- phase B (ROW): row `lane` -> 64 u -> keep; square -> forward -> tile ----------------
+    double U[32];
+    {
+      double hr[16], hi[16];
+      const double2* row = reinterpret_cast<const double2*>(tile) + lane * 15;
+#pragma unroll
+      for (int k = 1; k < 16; ++k) {
+        const double2 v = row[k - 1];
+        hr[k] = v.x;
+        hi[k] = v.y;
+      }
+      hr[0] = hi[0] = 0.0;
+      irfft32(0.0, hr, hi, U);
+      double s[32];
+#pragma unroll
+      for (int x = 0; x < 32; ++x) s[x] = U[x] * U[x];
+      double c0;
+      rfft32_fwd(s, c0, hr, hi);
+      double2* wrow = reinterpret_cast<double2*>(tile) + lane * 15;
+#pragma unroll
+      for (int k = 1; k < 16; ++k) wrow[k - 1] = make_double2(hr[k], hi[k]);
+    }
+    __syncwarp();
+    // ---------------- phase C (COL): N = 1/2 Dx(.) via the other component; stage 1; W = Dx F via the store ----------------
+    double s_ff = 0.0, s_mf = 0.0, s_x = 0.0, s_d = 0.0;
+    {
+      double x[32];
+      const double scl = 4.0 * sgq * cN;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) x[t] = scl * tile[(t * 15 + cc) * 2 + (1 - h)];
+      double n0, nr[16], ni[16];
+      rfft32_fwd(x, n0, nr, ni);
+      nr[0] = (0.5 * ks::kSqrt2) * n0;
+      ni[0] = 0.0;
+      static_for<0, 16>([&](auto Jc) {
+        constexpr int J = decltype(Jc)::value;
+        const bool pres = (J & 1) ? presO : presE;
+        const double w = (J == 0) ? 0.0 : wbase * (J * (1.0 / 32.0));
+        const double u1 = m1[J], u2 = m2[J];
+        double f1 = fma(d, u1, fma(-w, u2, nr[J]));
+        double f2 = (J == 0) ? 0.0 : fma(d, u2, fma(w, u1, ni[J]));
+        if constexpr (REL) {  // - (S/T) dx(u): a += sig q b, b -= sig q a  (partner's half via shuffle)
+          const double p1 = __shfl_xor_sync(0xffffffffu, u1, 1), p2 = __shfl_xor_sync(0xffffffffu, u2, 1);
+          f1 = fma(-sig * sgq, p1, f1);
+          if constexpr (J > 0) f2 = fma(-sig * sgq, p2, f2);
+          if constexpr (OP == KS_OP_COSTGRAD) {  // <dx u, F> pieces: this lane's F half against the partner's u half
+            s_d += sgq * (p1 * f1 + p2 * f2);
+          }
+        }
+        if (!pres) {
+          f1 = 0.0;
+          f2 = 0.0;
+        }
+        s_ff = fma(f1, f1, fma(f2, f2, s_ff));
+        if constexpr (OP == KS_OP_COSTGRAD) {
+          s_mf = fma(u1, f1, fma(u2, f2, s_mf));
+          s_x = fma(w, fma(u1, f2, -u2 * f1), s_x);
+        }
+        m1[J] = f1;
+        m2[J] = f2;
+      });
+      if constexpr (OP == KS_OP_EQN) {
+        double* Fp = a.out_state + (size_t)orbit * NM + coff;
+        static_for<0, 16>([&](auto Jc) {
+          constexpr int J = decltype(Jc)::value;
+          const bool pres = (J & 1) ? presO : presE;
+          if (colact && pres) {
+            Fp[J * COLS] = m1[J];
+            if constexpr (J > 0) Fp[(15 + J) * COLS] = m2[J];
+          }
+        });
+      } else {
+        if (a.f_out) {
+          double* Fp = a.f_out + (size_t)orbit * NM + coff;
+          static_for<0, 16>([&](auto Jc) {
+            constexpr int J = decltype(Jc)::value;
+            const bool pres = (J & 1) ? presO : presE;
+            if (colact && pres) {
+              Fp[J * COLS] = m1[J];
+              if constexpr (J > 0) Fp[(15 + J) * COLS] = m2[J];
+            }
+          });
+        }
+      }
+      // reductions over the 30 active lanes
+      const double lw = colact ? 1.0 : 0.0;
+      const double ff = warp_sum(s_ff * lw);
+      if (lane == 0 && a.out_cost) a.out_cost[orbit] = 0.5 * ff;
+      if constexpr (OP == KS_OP_COSTGRAD) {
+        const double e = 2.0 * q2 - 4.0 * q4;
+        // with <dx u, F> = s_d (summed over both halves): r_t ~ s_x - sig s_d, r_x ~ (e+d) s_mf + s_x - s_ff, r_s ~ s_d
+        double px = warp_sum(fma(e + d, s_mf, s_x - s_ff) * lw);
+        double pt = warp_sum(fma(-sig, s_d, s_x) * lw);
+        double ps = REL ? warp_sum(s_d * lw) : 0.0;
+        if (lane == 0 && (a.out_params || a.out_tail)) {
+          double gt = fix_t ? 0.0 : (-1.0 / T) * pt, gx = fix_x ? 0.0 : (1.0 / Lx) * px, gs = fix_s ? 0.0 : (-1.0 / T) * ps;
+          if constexpr (PC) {
+            if (!fix_t) gt *= 1.0 / T;
+            if (!fix_x) gx *= 1.0 / ((Lx * Lx) * (Lx * Lx));
+          }
+          if (a.out_tail) {
+            const int out_ld = a.out_ld ? a.out_ld : NM;
+            const double g3[3] = {gt, gx, gs};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int slot = ks::free_slot(a.cmask, i);
+              if (slot >= 0) a.out_state[(size_t)orbit * out_ld + NM + slot] = g3[i];
+            }
+          } else {
+            a.out_params[orbit * 3 + 0] = gt;
+            a.out_params[orbit * 3 + 1] = gx;
+            a.out_params[orbit * 3 + 2] = gs;
+          }
+        }
+      }
+      if constexpr (OP == KS_OP_EQN) continue;
+      // second inverse: spectrum of F's half -> its field component; Dx F = iq (A_F + i B_F): h0 writes q A_F to .y,
+      // h1 writes -q B_F to .x
+      double hr[16], hi[16];
+#pragma unroll
+      for (int J = 1; J < 16; ++J) {
+        hr[J] = m1[J];
+        hi[J] = m2[J];
+      }
+      hr[0] = hi[0] = 0.0;
+      irfft32(ks::kSqrt2 * m1[0], hr, hi, x);
+      const double sw = h ? -q : q;
+      if (colact) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) tile[(t * 15 + c) * 2 + (1 - h)] = sw * x[t];
+      }
+    }
+    __syncwarp();
+    // ---------------- phase D (ROW): second field times u -> forward -> tile ----------------
+    {
+      double hr[16], hi[16];
+      const double2* row = reinterpret_cast<const double2*>(tile) + lane * 15;
+#pragma unroll
+      for (int k = 1; k < 16; ++k) {
+        const double2 v = row[k - 1];
+        hr[k] = v.x;
+        hi[k] = v.y;
+      }
+      hr[0] = hi[0] = 0.0;
+      double w[32];
+      irfft32(0.0, hr, hi, w);
+#pragma unroll
+      for (int x = 0; x < 32; ++x) w[x] *= U[x];
+      double c0;
+      rfft32_fwd(w, c0, hr, hi);
+      double2* wrow = reinterpret_cast<double2*>(tile) + lane * 15;
+#pragma unroll
+      for (int k = 1; k < 16; ++k) wrow[k - 1] = make_double2(hr[k], hi[k]);
+    }
+    __syncwarp();
+    // ---------------- phase E (COL): stage 2: grad = -F_t + F_xx + F_xxxx [+ (S/T) F_x] - T(Fx(u w)) ----------------
+    {
+      double x[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) x[t] = (4.0 * cP) * tile[(t * 15 + cc) * 2 + h];
+      double p0, pr[16], pi[16];
+      rfft32_fwd(x, p0, pr, pi);
+      pr[0] = (0.5 * ks::kSqrt2) * p0;
+      pi[0] = 0.0;
+      const int out_ld = a.out_ld ? a.out_ld : NM;
+      double* Op = a.out_state + (size_t)orbit * out_ld + coff;
+      static_for<0, 16>([&](auto Jc) {
+        constexpr int J = decltype(Jc)::value;
+        const bool pres = (J & 1) ? presO : presE;
+        const double w = (J == 0) ? 0.0 : wbase * (J * (1.0 / 32.0));
+        const double f1 = m1[J], f2 = m2[J];
+        double g1 = fma(d, f1, fma(w, f2, -pr[J]));
+        double g2 = (J == 0) ? 0.0 : fma(d, f2, fma(-w, f1, -pi[J]));
+        if constexpr (REL) {  // + (S/T) dx(F)
+          const double p1 = __shfl_xor_sync(0xffffffffu, f1, 1), p2 = __shfl_xor_sync(0xffffffffu, f2, 1);
+          g1 = fma(sig * sgq, p1, g1);
+          if constexpr (J > 0) g2 = fma(sig * sgq, p2, g2);
+        }
+        if constexpr (PC) {
+          const double pm = 1.0 / ((w < 0 ? -w : w) + q2 + q4);
+          g1 *= pm;
+          g2 *= pm;
+        }
+        if (colact && pres) {
+          Op[J * COLS] = g1;
+          if constexpr (J > 0) Op[(15 + J) * COLS] = g2;
+        }
+      });
+    }
+    __syncwarp();  // the tile is rewritten by the next orbit's phase A (other lanes' columns are read in phase E)
+  }
+}
+
+}  // namespace ksx1
