@@ -92,16 +92,21 @@ int launch_warp32_as(const KsEvalArgs& a, cudaStream_t s) {
 template <int CLS, int OP, bool PC>
 int launch_warp32x1_pc(const KsEvalArgs& a, cudaStream_t s) {
   auto kern = ksx1::ks_warp32x1_kernel<CLS, OP, PC>;
+  constexpr int smem = ksx1::smem_bytes(OP == KS_OP_ADJSTEP);
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ksx1::kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(warp32x1) failed");
     attr_done = true;
   }
   const int ctas = (a.batch + ksx1::kWarpsPerCta - 1) / ksx1::kWarpsPerCta;
   const int sms = sm_count();
-  KS_LAUNCH(kern, ctas < sms ? ctas : sms, ksx1::kWarpsPerCta * 32, ksx1::kSmemBytes, s, a);
+  KS_LAUNCH(kern, ctas < sms ? ctas : sms, ksx1::kWarpsPerCta * 32, smem, s, a);
   return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32x1 kernel launch failed");
+}
+template <int CLS>
+int launch_adjstep(const KsEvalArgs& a, cudaStream_t s) {
+  return a.precond ? launch_warp32x1_pc<CLS, KS_OP_ADJSTEP, true>(a, s) : launch_warp32x1_pc<CLS, KS_OP_ADJSTEP, false>(a, s);
 }
 template <int CLS, int OP>
 int launch_warp32(const KsEvalArgs& a, cudaStream_t s) {
@@ -325,6 +330,25 @@ int ks_deriv(int cls, int n, int m, int batch, int axis, int order, int rows, in
 
 // ---- adjoint descent driver (reference optimize.py:367-509) ------------------------------------------------------
 namespace {
+// fused path (32x32, x1 kernel): per-orbit selection of the accepted ping-pong buffer into the caller's arrays
+__global__ void adj_gather_kernel(const KsAdjFused A, double* modes, double* params, int batch, int nm) {
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  const int cur = A.cur[b];
+  const double* src = A.u[cur] + (size_t)b * nm;
+  for (int i = threadIdx.x; i < nm; i += blockDim.x) modes[(size_t)b * nm + i] = src[i];
+  if (threadIdx.x < 3) params[b * 3 + threadIdx.x] = A.p[cur][b * 3 + threadIdx.x];
+}
+__global__ void adj_fused_init_kernel(int* status, int* nit, int* live, int* cur, double* step, double step0, int batch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch) {
+    status[i] = -1;
+    nit[i] = 0;
+    live[i] = 1;
+    cur[i] = 0;
+    step[i] = step0;
+  }
+}
 __global__ void adj_init_kernel(int* status, int* nit, int* live, double* step, double step0, int batch) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < batch) {
@@ -345,7 +369,10 @@ size_t ks_adjoint_descent_workspace_bytes(int cls, int n, int m, int batch) {
   bytes += 3 * align256((size_t)batch * 3 * 8);    // gp, trial params, trial gp
   bytes += align256((size_t)batch * 8);            // trial cost
   bytes += align256((size_t)batch * 4) + 256;      // live flags, live counter
-  return bytes;
+  // fused 32x32 path: ping-pong u / g / params / gradient-params, trial cost, cur flags
+  size_t fused = 4 * align256((size_t)batch * nm * 8) + 4 * align256((size_t)batch * 24) + align256((size_t)batch * 8) +
+                 2 * align256((size_t)batch * 4) + 256;
+  return bytes > fused ? bytes : fused;
 }
 
 int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* params, uint32_t cmask, double tol,
@@ -362,14 +389,69 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t nm = (size_t)(n - 1) * mode_cols(cls, m);
   unsigned char* p = static_cast<unsigned char*>(ws);
-  const size_t eval_bytes = ks_workspace_bytes(cls, n, m, batch);
-  void* eval_ws = p;
-  p += align256(eval_bytes);
   auto take = [&](size_t bytes) {
     void* q = p;
     p += align256(bytes);
     return q;
   };
+  if (check_every <= 0) check_every = 64;
+  if (use_warp32(n, m) && g_warp32_variant == 4) {
+    // ---- fused path: ONE launch per pass (decide on the previous trial + evaluate the next one inside the x1 kernel)
+    KsEvalArgs a;
+    std::memset(&a, 0, sizeof(a));
+    KsAdjFused& A = a.adj;
+    for (int i = 0; i < 2; ++i) A.u[i] = static_cast<double*>(take(batch * nm * 8));
+    for (int i = 0; i < 2; ++i) A.g[i] = static_cast<double*>(take(batch * nm * 8));
+    for (int i = 0; i < 2; ++i) A.p[i] = static_cast<double*>(take((size_t)batch * 24));
+    for (int i = 0; i < 2; ++i) A.gp[i] = static_cast<double*>(take((size_t)batch * 24));
+    A.tcost = static_cast<double*>(take((size_t)batch * 8));
+    A.live = static_cast<int*>(take((size_t)batch * 4));
+    A.cur = static_cast<int*>(take((size_t)batch * 4));
+    A.n_live = static_cast<int*>(take(4));
+    A.cost = cost_out;
+    A.step = step_out;
+    A.status = status_out;
+    A.nit = nit_out;
+    A.tol = tol;
+    A.ftol = ftol;
+    A.min_step = min_step;
+    A.maxiter = maxiter;
+    a.batch = batch;
+    a.cmask = cmask;
+    a.precond = preconditioning;
+    KS_LAUNCH(adj_fused_init_kernel, (batch + 255) / 256, 256, 0, s, status_out, nit_out, A.live, A.cur, step_out, step_size, batch);
+    cudaMemcpyAsync(A.u[0], modes, batch * nm * 8, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(A.p[0], params, (size_t)batch * 24, cudaMemcpyDeviceToDevice, s);
+    cudaMemsetAsync(A.g[0], 0, batch * nm * 8, s);
+    cudaMemsetAsync(A.gp[0], 0, (size_t)batch * 24, s);
+    const long max_passes = (long)maxiter + 1200;
+    int passes = 0;
+    for (long it = 0; it < max_passes; ++it) {
+      cudaMemsetAsync(A.n_live, 0, 4, s);
+      A.first = (it == 0) ? 1 : 0;
+      int rc;
+      switch (cls) {
+        case KS_ORBIT: rc = launch_adjstep<KS_ORBIT>(a, s); break;
+        case KS_RELATIVE: rc = launch_adjstep<KS_RELATIVE>(a, s); break;
+        case KS_SHIFT_REFLECTION: rc = launch_adjstep<KS_SHIFT_REFLECTION>(a, s); break;
+        default: rc = launch_adjstep<KS_ANTISYMMETRIC>(a, s); break;
+      }
+      if (rc != 0) return rc;
+      ++passes;
+      if ((it + 1) % check_every == 0 || it + 1 == max_passes) {
+        int n_live = 0;
+        if (cudaMemcpyAsync(&n_live, A.n_live, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+          return fail(KS_ERR_LAUNCH, "adjoint descent: device error while polling the live-orbit counter");
+        if (n_live == 0) break;
+      }
+    }
+    KS_LAUNCH(adj_gather_kernel, batch, 128, 0, s, A, modes, params, batch, (int)nm);
+    if (passes_out) *passes_out = passes;
+    return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "fused adjoint descent launch failed");
+  }
+  const size_t eval_bytes = ks_workspace_bytes(cls, n, m, batch);
+  void* eval_ws = p;
+  p += align256(eval_bytes);
   ksadj::AdjState st;
   st.u = modes;
   st.up = params;
@@ -397,7 +479,6 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
   cudaMemcpyAsync(st.tup, params, (size_t)batch * 24, cudaMemcpyDeviceToDevice, s);
   cudaMemsetAsync(st.g, 0, batch * nm * 8, s);
   cudaMemsetAsync(st.gp, 0, (size_t)batch * 24, s);
-  if (check_every <= 0) check_every = 64;
   // every live orbit either counts an iteration or halves its step in each pass: steps halve at most ~1100 times
   // before underflow and far fewer before min_step, iterations stop at maxiter
   const long max_passes = (long)maxiter + 1200;

@@ -8,9 +8,30 @@
 // :3582, :3189).  Numbering is shared with include/ks_b200.h and oracle/ks_oracle.py.
 enum { KS_ORBIT = 0, KS_RELATIVE = 1, KS_SHIFT_REFLECTION = 2, KS_ANTISYMMETRIC = 3 };
 // fused evaluation ops
-enum { KS_OP_EQN = 0, KS_OP_COSTGRAD = 1, KS_OP_MATVEC = 2, KS_OP_RMATVEC = 3 };
+enum { KS_OP_EQN = 0, KS_OP_COSTGRAD = 1, KS_OP_MATVEC = 2, KS_OP_RMATVEC = 3, KS_OP_ADJSTEP = 5 };
 // constraint mask bits (set = parameter held constant; reference core.py:1617-1664 `constraints`)
 enum { KS_FIX_T = 1, KS_FIX_X = 2, KS_FIX_S = 4 };
+
+// State of the fused adjoint-descent pass (one launch = decide on the previous trial + evaluate the next one, per orbit).
+// u/g/p/gp are ping-pong buffers: index cur[b] holds the accepted orbit of orbit b and the gradient there, the other
+// index receives the trial point and its gradient (an accepted step is then just cur[b] ^= 1, no copy).
+struct KsAdjFused {
+  double* u[2];    // [B, Nm]
+  double* g[2];    // [B, Nm]
+  double* p[2];    // [B, 3]
+  double* gp[2];   // [B, 3]
+  double* cost;    // [B]  cost at u[cur]
+  double* tcost;   // [B]  cost at the last trial
+  double* step;    // [B]
+  int* status;     // [B]
+  int* nit;        // [B]
+  int* live;       // [B]
+  int* cur;        // [B]
+  int* n_live;     // [1]
+  double tol, ftol, min_step;
+  int maxiter;
+  int first;       // first pass: evaluate u itself (initial cost and gradient), nothing to decide
+};
 
 struct KsEvalArgs {
   const double* modes;    // [B, Nm]   u in the modes basis
@@ -30,6 +51,7 @@ struct KsEvalArgs {
   int v_ld, out_ld;
   int v_tail;             // matvec: read (dT, dL, dS) from vmodes[b*v_ld + Nm + slot] instead of vparams
   int out_tail;           // rmatvec/costgrad: write free parameter components to out_state[b*out_ld + Nm + slot]
+  KsAdjFused adj;         // KS_OP_ADJSTEP only
 };
 
 namespace ks {

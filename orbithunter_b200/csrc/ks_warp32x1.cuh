@@ -25,8 +25,8 @@ using ksfft::sin64;
 constexpr int kWarpsPerCta = 8;
 constexpr int kTileDoubles = 32 * 15 * 2;  // XB tile of one orbit: 480 double2
 constexpr int kStageDoubles = 31 * 32;      // cp.async landing zone for the next orbit's half tuples (lane-private slots)
-constexpr int kWarpSmemDoubles = kTileDoubles + kStageDoubles;
-constexpr int kSmemBytes = kWarpsPerCta * kWarpSmemDoubles * 8;
+constexpr int warp_smem_doubles(bool adj) { return kTileDoubles + (adj ? 2 : 1) * kStageDoubles; }  // adj: u and g
+constexpr int smem_bytes(bool adj) { return kWarpsPerCta * warp_smem_doubles(adj) * 8; }
 
 // x[32] real -> c0 = DFT32(x)[0], (cr, ci)[k] = DFT32(x)[k], k = 1..15   (forward sign e^{-i...}, unnormalised).
 // ks_warp32.cuh's convention has the k >= 1 outputs doubled; here that factor (x2 per forward transform, x4 for the two
@@ -80,7 +80,10 @@ KS_DEVI double warp_sum(double v) {
 
 template <int CLS, int OP, bool PC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const KsEvalArgs a) {
-  static_assert(OP == KS_OP_EQN || OP == KS_OP_COSTGRAD, "this form implements eqn and costgrad");
+  static_assert(OP == KS_OP_EQN || OP == KS_OP_COSTGRAD || OP == KS_OP_ADJSTEP, "eqn, costgrad and the fused adjoint step");
+  constexpr bool ADJ = (OP == KS_OP_ADJSTEP);
+  constexpr bool GRAD = (OP == KS_OP_COSTGRAD) || ADJ;
+  constexpr int kWarpSmemDoubles = warp_smem_doubles(ADJ);
   constexpr bool FULL = (CLS == KS_ORBIT || CLS == KS_RELATIVE);
   constexpr bool REL = (CLS == KS_RELATIVE);
   constexpr int COLS = FULL ? 30 : 15, NM = 31 * COLS;
@@ -102,36 +105,106 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
 
   // u's half tuples reach the registers through a cp.async landing zone filled one orbit ahead (the first-touch DRAM
   // latency of the modes was 26 % of the warp-issue samples with plain loads: profiles/r01g_*)
-  auto prefetch = [&](int orb) {
-    if (orb < a.batch) {
-      const double* Mn = a.modes + (size_t)orb * NM + coff;
+  struct Pending {  // what the next iteration needs to know about its orbit (all lanes hold the same values)
+    int live, cur;
+    double step, T, L, S;
+  };
+  // fused adjoint descent: judge the previous trial of orbit `orb` (optimize.py:478-480 backtracking, then
+  // _process_correction :2174-2189 and the loop exit fix-up :506-507), publish the scalars, return what to evaluate next
+  auto decide = [&](int orb) {
+    Pending pd{0, 0, 0.0, 1.0, 1.0, 0.0};
+    if (orb >= a.batch) return pd;
+    if constexpr (ADJ) {
+      const KsAdjFused& A = a.adj;
+      int live = A.live[orb], cur = A.cur[orb];
+      double step = A.step[orb];
+      const double ct = A.tcost[orb];
+      double cost = A.cost[orb];
+      int status = A.status[orb], nit = A.nit[orb], accept = 0;
+      __syncwarp();  // every lane has read the scalars before lane 0 publishes the updated ones
+      if (live && !A.first && ct >= 0.0) {  // tcost < 0: no trial has been evaluated yet (pass right after the first)
+        if (ct >= cost && step > A.min_step) {
+          step *= 0.5;
+        } else {
+          nit += 1;
+          if (ct <= A.tol) {
+            status = -1;
+            accept = 1;
+          } else if (step <= A.min_step) {
+            status = 0;
+          } else if (nit == A.maxiter) {
+            status = 2;
+            accept = (ct < cost) ? 1 : 0;
+          } else {
+            const double big = fmax(fmax(cost, ct), 1.0);
+            if ((cost - ct) / big < A.ftol) status = 3; else accept = 1;
+          }
+          if (accept) {
+            cost = ct;
+            cur ^= 1;
+          }
+          live = (cost > A.tol && status == -1) ? 1 : 0;
+          if (!live && cost <= A.tol) status = -1;
+        }
+        if (lane == 0) {
+          A.cost[orb] = cost;
+          A.step[orb] = step;
+          A.status[orb] = status;
+          A.nit[orb] = nit;
+          A.live[orb] = live;
+          A.cur[orb] = cur;
+        }
+      }
+      pd.live = live;
+      pd.cur = cur;
+      pd.step = A.first ? 0.0 : step;
+      if (live) {
+        if (lane == 0 && !A.first) atomicAdd(A.n_live, 1);
+        const double* pp = A.p[cur] + orb * 3;
+        const double* gg = A.gp[cur] + orb * 3;
+        pd.T = fma(-pd.step, gg[0], pp[0]);
+        pd.L = fma(-pd.step, gg[1], pp[1]);
+        pd.S = fma(-pd.step, gg[2], pp[2]);
+      }
+    } else {
+      pd.live = 1;
+      pd.T = a.params[orb * 3 + 0];
+      pd.L = a.params[orb * 3 + 1];
+      pd.S = a.params[orb * 3 + 2];
+    }
+    return pd;
+  };
+  auto prefetch = [&](int orb, const Pending& pd) {
+    if (orb < a.batch && pd.live) {
+      const double* Mn = (ADJ ? a.adj.u[pd.cur] : a.modes) + (size_t)orb * NM + coff;
+      const double* Gn = ADJ ? a.adj.g[pd.cur] + (size_t)orb * NM + coff : nullptr;
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
         const bool pres = (J & 1) ? presO : presE;
         if (pres) {
           ksw32::cp_async8(stage + (J == 0 ? 0 : 2 * J - 1) * 32, Mn + J * COLS);
           if constexpr (J > 0) ksw32::cp_async8(stage + (2 * J) * 32, Mn + (15 + J) * COLS);
+          if constexpr (ADJ) {
+            ksw32::cp_async8(stage + kStageDoubles + (J == 0 ? 0 : 2 * J - 1) * 32, Gn + J * COLS);
+            if constexpr (J > 0) ksw32::cp_async8(stage + kStageDoubles + (2 * J) * 32, Gn + (15 + J) * COLS);
+          }
         }
       });
     }
     ksw32::cp_async_commit();
   };
-  prefetch(gw);
-  // parameters of the next orbit are fetched one iteration ahead as well (three plain loads held in registers)
-  double nT = 1.0, nL = 1.0, nS = 0.0;
-  if (gw < a.batch) {
-    nT = a.params[gw * 3 + 0];
-    nL = a.params[gw * 3 + 1];
-    nS = a.params[gw * 3 + 2];
-  }
+  Pending next = decide(gw);
+  prefetch(gw, next);
 #pragma unroll 1
   for (int orbit = gw; orbit < a.batch; orbit += nw) {
-    const double T = nT, Lx = nL, S = nS;
-    if (orbit + nw < a.batch) {
-      nT = a.params[(orbit + nw) * 3 + 0];
-      nL = a.params[(orbit + nw) * 3 + 1];
-      nS = a.params[(orbit + nw) * 3 + 2];
+    const Pending pd = next;
+    next = decide(orbit + nw);
+    if (!pd.live) {  // (fused adjoint descent) this orbit has left the loop: nothing was staged for it
+      ksw32::cp_async_wait<0>();
+      prefetch(orbit + nw, next);
+      continue;
     }
+    const double T = pd.T, Lx = pd.L, S = pd.S;
     const double wbase = -1.0 * (ks::kTwoPi * 32.0 / T);
     const double q = (ks::kTwoPi * 32.0 / Lx) * ((cc + 1) * (1.0 / 32.0));
     const double q2 = q * q, q4 = q2 * q2, d = q4 - q2;
@@ -146,8 +219,35 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
       const bool pres = (J & 1) ? presO : presE;
       m1[J] = pres ? stage[(J == 0 ? 0 : 2 * J - 1) * 32] : 0.0;
       if constexpr (J > 0) m2[J] = pres ? stage[(2 * J) * 32] : 0.0; else m2[J] = 0.0;
+      if constexpr (ADJ) {  // trial point u - step * grad (core.py:1760-1796 increment), kept as the next candidate
+        const double g1 = pres ? stage[kStageDoubles + (J == 0 ? 0 : 2 * J - 1) * 32] : 0.0;
+        m1[J] = fma(-pd.step, g1, m1[J]);
+        if constexpr (J > 0) {
+          const double g2 = pres ? stage[kStageDoubles + (2 * J) * 32] : 0.0;
+          m2[J] = fma(-pd.step, g2, m2[J]);
+        }
+      }
     });
-    prefetch(orbit + nw);
+    if constexpr (ADJ) {
+      if (!a.adj.first) {
+        double* Tp = a.adj.u[pd.cur ^ 1] + (size_t)orbit * NM + coff;
+        static_for<0, 16>([&](auto Jc) {
+          constexpr int J = decltype(Jc)::value;
+          const bool pres = (J & 1) ? presO : presE;
+          if (colact && pres) {
+            Tp[J * COLS] = m1[J];
+            if constexpr (J > 0) Tp[(15 + J) * COLS] = m2[J];
+          }
+        });
+        if (lane == 0) {
+          double* tp = a.adj.p[pd.cur ^ 1] + orbit * 3;
+          tp[0] = T;
+          tp[1] = Lx;
+          tp[2] = S;
+        }
+      }
+    }
+    prefetch(orbit + nw, next);
     {
       double x[32];
       double hr[16], hi[16];
@@ -209,7 +309,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
           const double p1 = __shfl_xor_sync(0xffffffffu, u1, 1), p2 = __shfl_xor_sync(0xffffffffu, u2, 1);
           f1 = fma(-sig * sgq, p1, f1);
           if constexpr (J > 0) f2 = fma(-sig * sgq, p2, f2);
-          if constexpr (OP == KS_OP_COSTGRAD) {  // <dx u, F> pieces: this lane's F half against the partner's u half
+          if constexpr (GRAD) {  // <dx u, F> pieces: this lane's F half against the partner's u half
             s_d += sgq * (p1 * f1 + p2 * f2);
           }
         }
@@ -218,7 +318,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
           f2 = 0.0;
         }
         s_ff = fma(f1, f1, fma(f2, f2, s_ff));
-        if constexpr (OP == KS_OP_COSTGRAD) {
+        if constexpr (GRAD) {
           s_mf = fma(u1, f1, fma(u2, f2, s_mf));
           s_x = fma(w, fma(u1, f2, -u2 * f1), s_x);
         }
@@ -235,7 +335,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
             if constexpr (J > 0) Fp[(15 + J) * COLS] = m2[J];
           }
         });
-      } else {
+      } else if constexpr (OP == KS_OP_COSTGRAD) {
         if (a.f_out) {
           double* Fp = a.f_out + (size_t)orbit * NM + coff;
           static_for<0, 16>([&](auto Jc) {
@@ -251,20 +351,41 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
       // reductions over the 30 active lanes
       const double lw = colact ? 1.0 : 0.0;
       const double ff = warp_sum(s_ff * lw);
-      if (lane == 0 && a.out_cost) a.out_cost[orbit] = 0.5 * ff;
-      if constexpr (OP == KS_OP_COSTGRAD) {
+      if constexpr (ADJ) {
+        if (lane == 0) {
+          const KsAdjFused& A = a.adj;
+          if (A.first) {  // initial F and cost (optimize.py:462-463); the while-condition cost > tol (:467)
+            const double c0 = 0.5 * ff;
+            A.cost[orbit] = c0;
+            A.tcost[orbit] = -1.0;  // "no trial pending" marker for the next pass
+            const int lv = c0 > A.tol ? 1 : 0;
+            A.live[orbit] = lv;
+            if (lv) atomicAdd(A.n_live, 1);
+          } else {
+            A.tcost[orbit] = 0.5 * ff;
+          }
+        }
+      } else {
+        if (lane == 0 && a.out_cost) a.out_cost[orbit] = 0.5 * ff;
+      }
+      if constexpr (GRAD) {
         const double e = 2.0 * q2 - 4.0 * q4;
         // with <dx u, F> = s_d (summed over both halves): r_t ~ s_x - sig s_d, r_x ~ (e+d) s_mf + s_x - s_ff, r_s ~ s_d
         double px = warp_sum(fma(e + d, s_mf, s_x - s_ff) * lw);
         double pt = warp_sum(fma(-sig, s_d, s_x) * lw);
         double ps = REL ? warp_sum(s_d * lw) : 0.0;
-        if (lane == 0 && (a.out_params || a.out_tail)) {
+        if (lane == 0 && (ADJ || a.out_params || a.out_tail)) {
           double gt = fix_t ? 0.0 : (-1.0 / T) * pt, gx = fix_x ? 0.0 : (1.0 / Lx) * px, gs = fix_s ? 0.0 : (-1.0 / T) * ps;
           if constexpr (PC) {
             if (!fix_t) gt *= 1.0 / T;
             if (!fix_x) gx *= 1.0 / ((Lx * Lx) * (Lx * Lx));
           }
-          if (a.out_tail) {
+          if constexpr (ADJ) {
+            double* gpp = a.adj.gp[a.adj.first ? pd.cur : pd.cur ^ 1] + orbit * 3;
+            gpp[0] = gt;
+            gpp[1] = gx;
+            gpp[2] = gs;
+          } else if (a.out_tail) {
             const int out_ld = a.out_ld ? a.out_ld : NM;
             const double g3[3] = {gt, gx, gs};
 #pragma unroll
@@ -329,7 +450,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
       pr[0] = (0.5 * ks::kSqrt2) * p0;
       pi[0] = 0.0;
       const int out_ld = a.out_ld ? a.out_ld : NM;
-      double* Op = a.out_state + (size_t)orbit * out_ld + coff;
+      double* Op = ADJ ? a.adj.g[a.adj.first ? pd.cur : pd.cur ^ 1] + (size_t)orbit * NM + coff
+                       : a.out_state + (size_t)orbit * out_ld + coff;
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
         const bool pres = (J & 1) ? presO : presE;

@@ -1,0 +1,54 @@
+"""Side measurements (not the bench.py contract): evals/s of the fused costgrad and of matvec/rmatvec at the other
+BASELINE shapes, through BatchedOrbitKS, CUDA-event timed.  python tools_bench_shapes.py"""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from orbithunter_b200 import BatchedOrbitKS  # noqa: E402
+from orbithunter_b200.ks import CLASSES  # noqa: E402
+
+
+def seeds(cls, n, m, T, L, B):
+    base = np.stack([CLASSES[cls](parameters=(T, L, 0.0)).populate(attr="state", seed=s, discretization=(n, m)).state
+                     for s in range(min(B, 16))])
+    reps = (B + base.shape[0] - 1) // base.shape[0]
+    return np.tile(base, (reps, 1, 1))[:B] * (1.0 + 1e-3 * np.arange(B)[:, None, None] / B)
+
+
+def timeit(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+out = []
+for cls, n, m, T, L, B in (("OrbitKS", 32, 32, 44.0, 33.4, 4096), ("RelativeOrbitKS", 64, 64, 60.0, 44.0, 4096),
+                           ("ShiftReflectionOrbitKS", 64, 64, 60.0, 44.0, 4096), ("AntisymmetricOrbitKS", 64, 64, 60.0, 44.0, 4096),
+                           ("OrbitKS", 256, 256, 200.0, 200.0, 64)):
+    M = seeds(cls, n, m, T, L, B)
+    p = np.tile([T, L, 0.0], (B, 1))
+    u = BatchedOrbitKS(M, p, cls)
+    v = BatchedOrbitKS(np.random.RandomState(0).randn(*M.shape), np.random.RandomState(1).randn(B, 3), cls)
+    nm = M.shape[1] * M.shape[2]
+    rec = {"class": cls, "grid": [n, m], "batch": B}
+    ms = timeit(lambda: u.costgrad(), 20)
+    rec["costgrad_evals_per_s"] = B / ms * 1e3
+    rec["costgrad_alg_GBps"] = B * 8 * (2 * nm + 7) / ms / 1e6
+    ms = timeit(lambda: u.matvec(v), 20)
+    rec["matvec_per_s"] = B / ms * 1e3
+    ms = timeit(lambda: u.rmatvec(v), 20)
+    rec["rmatvec_per_s"] = B / ms * 1e3
+    rec["matvec_alg_GBps"] = B * 8 * (3 * nm + 9) / ms / 1e6
+    out.append(rec)
+    print(json.dumps(rec), flush=True)
