@@ -25,8 +25,8 @@ using ksfft::sin64;
 constexpr int kWarpsPerCta = 8;
 constexpr int kTileDoubles = 32 * 15 * 2;  // XB tile of one orbit: 480 double2
 constexpr int kStageDoubles = 31 * 32;      // cp.async landing zone for the next orbit's half tuples (lane-private slots)
-constexpr int warp_smem_doubles(bool adj) { return kTileDoubles + (adj ? 2 : 1) * kStageDoubles; }  // adj: u and g
-constexpr int smem_bytes(bool adj) { return kWarpsPerCta * warp_smem_doubles(adj) * 8; }
+KS_HD constexpr int warp_smem_doubles(bool adj) { return kTileDoubles + (adj ? 2 : 1) * kStageDoubles; }  // adj: u and g
+KS_HD constexpr int smem_bytes(bool adj) { return kWarpsPerCta * warp_smem_doubles(adj) * 8; }
 
 // x[32] real -> c0 = DFT32(x)[0], (cr, ci)[k] = DFT32(x)[k], k = 1..15   (forward sign e^{-i...}, unnormalised).
 // ks_warp32.cuh's convention has the k >= 1 outputs doubled; here that factor (x2 per forward transform, x4 for the two
