@@ -331,12 +331,39 @@ int ks_deriv(int cls, int n, int m, int batch, int axis, int order, int rows, in
 // ---- adjoint descent driver (reference optimize.py:367-509) ------------------------------------------------------
 namespace {
 // fused path (32x32, x1 kernel): per-orbit selection of the accepted ping-pong buffer into the caller's arrays
-__global__ void adj_gather_kernel(const KsAdjFused A, double* modes, double* params, int batch, int nm) {
+// user layout [rows][cols] <-> packed lane-major layout of ks_warp32x1.cuh (lane = 2 c + h, slot 0 = x1(0),
+// slot 2J-1 = x1(J) (row J), slot 2J = x2(J) (row 15+J); half classes: a-halves exist for odd J, b-halves for even J
+// (ShiftReflection) or b-halves only (Antisymmetric))
+__device__ __host__ inline int packed_user_index(int cls, int lane, int slot) {
+  const int c = lane >> 1, h = lane & 1;
+  if (c >= 15 || slot > 30) return -1;
+  const int J = (slot + 1) >> 1, second = (slot > 0 && (slot & 1) == 0) ? 1 : 0;
+  const bool full = (cls == KS_ORBIT || cls == KS_RELATIVE);
+  if (!full) {
+    const bool pres = (cls == KS_ANTISYMMETRIC) ? (h == 1) : ((J & 1) ? h == 0 : h == 1);
+    if (!pres) return -1;
+  }
+  const int cols = full ? 30 : 15;
+  return (second ? 15 + J : J) * cols + (full ? h * 15 : 0) + c;
+}
+__global__ void adj_pack_kernel(const double* modes, double* packed, int cls, int batch, int nm) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < ksx1::kPackedDoubles; i += blockDim.x) {
+    const int pr = i / 64, r = i - pr * 64, lane = r >> 1, slot = 2 * pr + (r & 1);
+    const int ui = packed_user_index(cls, lane, slot);
+    packed[(size_t)b * ksx1::kPackedDoubles + i] = ui >= 0 ? modes[(size_t)b * nm + ui] : 0.0;
+  }
+}
+__global__ void adj_gather_kernel(const KsAdjFused A, double* modes, double* params, int cls, int batch, int nm) {
   const int b = blockIdx.x;
   if (b >= batch) return;
   const int cur = A.cur[b];
-  const double* src = A.u[cur] + (size_t)b * nm;
-  for (int i = threadIdx.x; i < nm; i += blockDim.x) modes[(size_t)b * nm + i] = src[i];
+  const double* src = A.u[cur] + (size_t)b * ksx1::kPackedDoubles;
+  for (int i = threadIdx.x; i < ksx1::kPackedDoubles; i += blockDim.x) {
+    const int pr = i / 64, r = i - pr * 64, lane = r >> 1, slot = 2 * pr + (r & 1);
+    const int ui = packed_user_index(cls, lane, slot);
+    if (ui >= 0) modes[(size_t)b * nm + ui] = src[i];
+  }
   if (threadIdx.x < 3) params[b * 3 + threadIdx.x] = A.p[cur][b * 3 + threadIdx.x];
 }
 __global__ void adj_fused_init_kernel(int* status, int* nit, int* live, int* cur, double* step, double step0, int batch) {
@@ -370,8 +397,8 @@ size_t ks_adjoint_descent_workspace_bytes(int cls, int n, int m, int batch) {
   bytes += align256((size_t)batch * 8);            // trial cost
   bytes += align256((size_t)batch * 4) + 256;      // live flags, live counter
   // fused 32x32 path: ping-pong u / g / params / gradient-params, trial cost, cur flags
-  size_t fused = 4 * align256((size_t)batch * nm * 8) + 4 * align256((size_t)batch * 24) + align256((size_t)batch * 8) +
-                 2 * align256((size_t)batch * 4) + 256;
+  size_t fused = 4 * align256((size_t)batch * ksx1::kPackedDoubles * 8) + 4 * align256((size_t)batch * 24) +
+                 align256((size_t)batch * 8) + 2 * align256((size_t)batch * 4) + 256;
   return bytes > fused ? bytes : fused;
 }
 
@@ -400,8 +427,9 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
     KsEvalArgs a;
     std::memset(&a, 0, sizeof(a));
     KsAdjFused& A = a.adj;
-    for (int i = 0; i < 2; ++i) A.u[i] = static_cast<double*>(take(batch * nm * 8));
-    for (int i = 0; i < 2; ++i) A.g[i] = static_cast<double*>(take(batch * nm * 8));
+    const size_t pbytes = (size_t)batch * ksx1::kPackedDoubles * 8;
+    for (int i = 0; i < 2; ++i) A.u[i] = static_cast<double*>(take(pbytes));
+    for (int i = 0; i < 2; ++i) A.g[i] = static_cast<double*>(take(pbytes));
     for (int i = 0; i < 2; ++i) A.p[i] = static_cast<double*>(take((size_t)batch * 24));
     for (int i = 0; i < 2; ++i) A.gp[i] = static_cast<double*>(take((size_t)batch * 24));
     A.tcost = static_cast<double*>(take((size_t)batch * 8));
@@ -420,9 +448,9 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
     a.cmask = cmask;
     a.precond = preconditioning;
     KS_LAUNCH(adj_fused_init_kernel, (batch + 255) / 256, 256, 0, s, status_out, nit_out, A.live, A.cur, step_out, step_size, batch);
-    cudaMemcpyAsync(A.u[0], modes, batch * nm * 8, cudaMemcpyDeviceToDevice, s);
+    KS_LAUNCH(adj_pack_kernel, batch, 128, 0, s, (const double*)modes, A.u[0], cls, batch, (int)nm);
     cudaMemcpyAsync(A.p[0], params, (size_t)batch * 24, cudaMemcpyDeviceToDevice, s);
-    cudaMemsetAsync(A.g[0], 0, batch * nm * 8, s);
+    cudaMemsetAsync(A.g[0], 0, pbytes, s);
     cudaMemsetAsync(A.gp[0], 0, (size_t)batch * 24, s);
     const long max_passes = (long)maxiter + 1200;
     int passes = 0;
@@ -445,7 +473,7 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
         if (n_live == 0) break;
       }
     }
-    KS_LAUNCH(adj_gather_kernel, batch, 128, 0, s, A, modes, params, batch, (int)nm);
+    KS_LAUNCH(adj_gather_kernel, batch, 128, 0, s, A, modes, params, cls, batch, (int)nm);
     if (passes_out) *passes_out = passes;
     return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "fused adjoint descent launch failed");
   }

@@ -24,8 +24,9 @@ using ksfft::sin64;
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kTileDoubles = 32 * 15 * 2;  // XB tile of one orbit: 480 double2
+constexpr int kPackedDoubles = 16 * 32 * 2;  // per orbit, packed lane-major layout of the fused adjoint pass (below)
 constexpr int kStageDoubles = 31 * 32;      // cp.async landing zone for the next orbit's half tuples (lane-private slots)
-KS_HD constexpr int warp_smem_doubles(bool adj) { return kTileDoubles + (adj ? 2 : 1) * kStageDoubles; }  // adj: u and g
+KS_HD constexpr int warp_smem_doubles(bool adj) { return kTileDoubles + (adj ? 2 * kPackedDoubles : kStageDoubles); }  // adj: u and g, packed
 KS_HD constexpr int smem_bytes(bool adj) { return kWarpsPerCta * warp_smem_doubles(adj) * 8; }
 
 // x[32] real -> c0 = DFT32(x)[0], (cr, ci)[k] = DFT32(x)[k], k = 1..15   (forward sign e^{-i...}, unnormalised).
@@ -69,6 +70,19 @@ KS_DEVI void irfft32(double h0, const double (&hr)[16], const double (&hi)[16], 
   }
 }
 
+// Packed lane-major layout of the fused adjoint pass' internal orbit / gradient buffers: per orbit 16 pairs x 32 lanes of
+// double2; pair pr of lane l holds slots (2 pr, 2 pr + 1) of that lane's 31 half-tuple values (slot 0 = x1(0), slot 2J-1 =
+// x1(J), slot 2J = x2(J)).  One 16-byte access per pair instead of two strided 8-byte ones.
+KS_DEVI void cp_async16(double* smem_dst, const double* gsrc) {
+#ifdef KS_HOST_EMUL
+  smem_dst[0] = gsrc[0];
+  smem_dst[1] = gsrc[1];
+#else
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+
 KS_DEVI double warp_sum(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 16);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -91,6 +105,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* tile = smem + warp * kWarpSmemDoubles;  // tile[(t * 15 + c) * 2 + component]
   double* stage = tile + kTileDoubles + lane;     // slot s of this lane at stage[s * 32]
+  double* pstage = tile + kTileDoubles + lane * 2;  // packed variant (fused adjoint pass): pair pr at pstage[pr * 64]
   const int c = lane >> 1, h = lane & 1;
   const bool colact = c < 15;
   const int cc = colact ? c : 14;
@@ -176,20 +191,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
   };
   auto prefetch = [&](int orb, const Pending& pd) {
     if (orb < a.batch && pd.live) {
-      const double* Mn = (ADJ ? a.adj.u[pd.cur] : a.modes) + (size_t)orb * NM + coff;
-      const double* Gn = ADJ ? a.adj.g[pd.cur] + (size_t)orb * NM + coff : nullptr;
-      static_for<0, 16>([&](auto Jc) {
-        constexpr int J = decltype(Jc)::value;
-        const bool pres = (J & 1) ? presO : presE;
-        if (pres) {
-          ksw32::cp_async8(stage + (J == 0 ? 0 : 2 * J - 1) * 32, Mn + J * COLS);
-          if constexpr (J > 0) ksw32::cp_async8(stage + (2 * J) * 32, Mn + (15 + J) * COLS);
-          if constexpr (ADJ) {
-            ksw32::cp_async8(stage + kStageDoubles + (J == 0 ? 0 : 2 * J - 1) * 32, Gn + J * COLS);
-            if constexpr (J > 0) ksw32::cp_async8(stage + kStageDoubles + (2 * J) * 32, Gn + (15 + J) * COLS);
-          }
+      if constexpr (ADJ) {
+        const double* Un = a.adj.u[pd.cur] + (size_t)orb * kPackedDoubles + lane * 2;
+        const double* Gn = a.adj.g[pd.cur] + (size_t)orb * kPackedDoubles + lane * 2;
+#pragma unroll
+        for (int pr = 0; pr < 16; ++pr) {
+          cp_async16(pstage + pr * 64, Un + pr * 64);
+          cp_async16(pstage + kPackedDoubles + pr * 64, Gn + pr * 64);
         }
-      });
+      } else {
+        const double* Mn = a.modes + (size_t)orb * NM + coff;
+        static_for<0, 16>([&](auto Jc) {
+          constexpr int J = decltype(Jc)::value;
+          const bool pres = (J & 1) ? presO : presE;
+          if (pres) {
+            ksw32::cp_async8(stage + (J == 0 ? 0 : 2 * J - 1) * 32, Mn + J * COLS);
+            if constexpr (J > 0) ksw32::cp_async8(stage + (2 * J) * 32, Mn + (15 + J) * COLS);
+          }
+        });
+      }
     }
     ksw32::cp_async_commit();
   };
@@ -214,31 +234,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
     // ---------------- phase A (COL): half tuples of u -> A[t] or B[t] -> tile component h ----------------
     double m1[16], m2[16];  // half tuples (x1, x2) of u; overwritten by F in stage 1
     ksw32::cp_async_wait<0>();
-    static_for<0, 16>([&](auto Jc) {
-      constexpr int J = decltype(Jc)::value;
-      const bool pres = (J & 1) ? presO : presE;
-      m1[J] = pres ? stage[(J == 0 ? 0 : 2 * J - 1) * 32] : 0.0;
-      if constexpr (J > 0) m2[J] = pres ? stage[(2 * J) * 32] : 0.0; else m2[J] = 0.0;
-      if constexpr (ADJ) {  // trial point u - step * grad (core.py:1760-1796 increment), kept as the next candidate
-        const double g1 = pres ? stage[kStageDoubles + (J == 0 ? 0 : 2 * J - 1) * 32] : 0.0;
-        m1[J] = fma(-pd.step, g1, m1[J]);
-        if constexpr (J > 0) {
-          const double g2 = pres ? stage[kStageDoubles + (2 * J) * 32] : 0.0;
-          m2[J] = fma(-pd.step, g2, m2[J]);
-        }
+    if constexpr (ADJ) {
+      // trial point u - step * grad (core.py:1760-1796 increment); slot 2J-1 = x1(J), slot 2J = x2(J), slot 0 = x1(0)
+      m2[0] = 0.0;
+#pragma unroll
+      for (int pr = 0; pr < 16; ++pr) {
+        const double2 uu = *reinterpret_cast<const double2*>(pstage + pr * 64);
+        const double2 gg = *reinterpret_cast<const double2*>(pstage + kPackedDoubles + pr * 64);
+        const double lo = fma(-pd.step, gg.x, uu.x), hi = fma(-pd.step, gg.y, uu.y);
+        if (pr == 0) m1[0] = lo; else m2[pr] = lo;
+        if (pr < 15) m1[pr + 1] = hi;
       }
-    });
+    } else {
+      static_for<0, 16>([&](auto Jc) {
+        constexpr int J = decltype(Jc)::value;
+        const bool pres = (J & 1) ? presO : presE;
+        m1[J] = pres ? stage[(J == 0 ? 0 : 2 * J - 1) * 32] : 0.0;
+        if constexpr (J > 0) m2[J] = pres ? stage[(2 * J) * 32] : 0.0; else m2[J] = 0.0;
+      });
+    }
     if constexpr (ADJ) {
       if (!a.adj.first) {
-        double* Tp = a.adj.u[pd.cur ^ 1] + (size_t)orbit * NM + coff;
-        static_for<0, 16>([&](auto Jc) {
-          constexpr int J = decltype(Jc)::value;
-          const bool pres = (J & 1) ? presO : presE;
-          if (colact && pres) {
-            Tp[J * COLS] = m1[J];
-            if constexpr (J > 0) Tp[(15 + J) * COLS] = m2[J];
-          }
-        });
+        double* Tp = a.adj.u[pd.cur ^ 1] + (size_t)orbit * kPackedDoubles + lane * 2;
+#pragma unroll
+        for (int pr = 0; pr < 16; ++pr)
+          *reinterpret_cast<double2*>(Tp + pr * 64) = make_double2(pr == 0 ? m1[0] : m2[pr], pr < 15 ? m1[pr + 1] : 0.0);
         if (lane == 0) {
           double* tp = a.adj.p[pd.cur ^ 1] + orbit * 3;
           tp[0] = T;
@@ -450,8 +470,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
       pr[0] = (0.5 * ks::kSqrt2) * p0;
       pi[0] = 0.0;
       const int out_ld = a.out_ld ? a.out_ld : NM;
-      double* Op = ADJ ? a.adj.g[a.adj.first ? pd.cur : pd.cur ^ 1] + (size_t)orbit * NM + coff
-                       : a.out_state + (size_t)orbit * out_ld + coff;
+      double* Op = ADJ ? nullptr : a.out_state + (size_t)orbit * out_ld + coff;
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
         const bool pres = (J & 1) ? presO : presE;
@@ -469,11 +488,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
           g1 *= pm;
           g2 *= pm;
         }
-        if (colact && pres) {
-          Op[J * COLS] = g1;
-          if constexpr (J > 0) Op[(15 + J) * COLS] = g2;
+        if constexpr (ADJ) {  // keep the gradient half tuples (absent halves as zeros) for the packed store below
+          m1[J] = pres ? g1 : 0.0;
+          m2[J] = pres ? g2 : 0.0;
+        } else {
+          if (colact && pres) {
+            Op[J * COLS] = g1;
+            if constexpr (J > 0) Op[(15 + J) * COLS] = g2;
+          }
         }
       });
+      if constexpr (ADJ) {
+        double* Gp = a.adj.g[a.adj.first ? pd.cur : pd.cur ^ 1] + (size_t)orbit * kPackedDoubles + lane * 2;
+#pragma unroll
+        for (int pr = 0; pr < 16; ++pr)
+          *reinterpret_cast<double2*>(Gp + pr * 64) = make_double2(pr == 0 ? m1[0] : m2[pr], pr < 15 ? m1[pr + 1] : 0.0);
+      }
     }
     __syncwarp();  // the tile is rewritten by the next orbit's phase A (other lanes' columns are read in phase E)
   }
