@@ -39,6 +39,9 @@ void ks_debug_force_generic(int on);
 /* tuning hook, 32x32 kernel build variant: 3 = two orbits per warp, 7 warps/SM, global reads staged with cp.async
  * (all ops); 4 (default) = one orbit per warp, 8 warps/SM, all state in registers (eqn and costgrad; other ops use 3). */
 void ks_debug_warp32_variant(int variant);
+/* tuning hook, large-grid (n, m in {64, 128, 256}) tile path: enabled = 0 routes those shapes through the generic
+ * kernel (cross-check); chunk_mb > 0 sets the workspace budget that bounds how many orbits one pass sequence covers. */
+void ks_debug_tile(int enabled, int chunk_mb);
 
 /* rows*cols of the modes basis for (cls, n, m); 0 if the shape is not supported. */
 int ks_mode_size(int cls, int n, int m);

@@ -33,15 +33,18 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objs = []
-    for src in sources():
+    objs, procs = [], []
+    for src in sources():  # one nvcc per translation unit, all at once
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
         cmd = [NVCC, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "-I", CSRC, "-I", INCLUDE, "-c", src,
                "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        subprocess.check_call(cmd)
+        procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
     subprocess.check_call([NVCC, "-shared", *ARCH, "-o", LIB, *objs, "-lcudart"])
     return LIB
 

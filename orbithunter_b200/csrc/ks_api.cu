@@ -8,37 +8,15 @@
 #include "ks_common.cuh"
 #include "ks_generic.cuh"
 #include "ks_krylov.cuh"
+#include "ks_host.cuh"
+#include "ks_tile.cuh"
 #include "ks_warp32.cuh"
 #include "ks_warp32x1.cuh"
 
+using namespace ksh;
 namespace {
-thread_local char g_err[256] = "";
-int fail(int code, const char* msg) {
-  std::snprintf(g_err, sizeof(g_err), "%s", msg);
-  return code;
-}
-int sm_count() {
-#ifdef KS_HOST_EMUL
-  return ks_emul::device_sm_count;
-#else
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-    cached = n;
-  }
-  return cached;
-#endif
-}
 bool shape_ok(int cls, int n, int m) {
   return cls >= 0 && cls <= 3 && n >= 4 && m >= 4 && (n % 2 == 0) && (m % 2 == 0) && n <= 4096 && m <= 4096;
-}
-int mode_cols(int cls, int m) { return (cls == KS_ORBIT || cls == KS_RELATIVE) ? m - 2 : m / 2 - 1; }
-int ilog2_exact(int v) {
-  int l = 0;
-  while ((1 << l) < v) ++l;
-  return (1 << l) == v ? l : -1;
 }
 bool g_force_generic = false;  // debug/test switch: route 32x32 through the generic kernel as a cross-check
 int g_warp32_variant = 4;  // 3: two orbits per warp, cp.async staging (all ops); 4: one orbit per warp, register-resident (eqn, costgrad)  // which warp32 build variant to launch (see ks_warp32.cuh Cfg)
@@ -53,22 +31,6 @@ int generic_grid(int batch) {
   const int cap = 2 * sm_count();
   return batch < cap ? batch : cap;
 }
-ksg::Geom make_geom(int cls, int n, int m) {
-  ksg::Geom g;
-  g.n = n;
-  g.m = m;
-  g.h = n / 2 - 1;
-  g.k = m / 2 - 1;
-  g.cols = mode_cols(cls, m);
-  g.nm = (n - 1) * g.cols;
-  g.nmax = n > m ? n : m;
-  g.log_n = ilog2_exact(n);
-  g.log_m = ilog2_exact(m);
-  g.ct = 1.0 / sqrt(2.0 * n);
-  g.cx = 1.0 / sqrt(2.0 * m);
-  return g;
-}
-
 template <int CLS, int OP, bool PC>
 int launch_warp32_as_pc(const KsEvalArgs& a, cudaStream_t s) {
   using Cfg = ksw32::Cfg<false>;
@@ -131,6 +93,32 @@ int launch_generic(const ksg::GenArgs& ga, cudaStream_t s) {
   return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "generic kernel launch failed");
 }
 
+
+// ---- tile path (n, m in {64, 128, 256}): kernels and launch code live in ks_tile_c{0..3}.cu (one class per translation
+// unit, compiled in parallel); see ks_tile_host.cuh ----
+bool g_tile_enabled = true;
+int g_tile_chunk_mb = 64;
+bool use_tile(int n, int m) { return g_tile_enabled && !g_force_generic && kst::size_ok(n) && kst::size_ok(m); }
+int tile_chunk(int n, int m, int cols, int batch) {
+  const size_t per = kst::orbit_doubles(n, m, cols) * 8;
+  size_t c = ((size_t)g_tile_chunk_mb << 20) / per;
+  if (c < 1) c = 1;
+  return c < (size_t)batch ? (int)c : batch;
+}
+size_t tile_workspace_bytes(int n, int m, int cols, int batch) {
+  return (size_t)tile_chunk(n, m, cols, batch) * kst::orbit_doubles(n, m, cols) * 8 + 4 * 256;
+}
+template <int OP>
+int launch_tile(int cls, int n, int m, const KsEvalArgs& a, cudaStream_t s) {
+  const int chunk = tile_chunk(n, m, mode_cols(cls, m), a.batch);
+  switch (cls) {
+    case KS_ORBIT: return ks_tile_run_c0(OP, n, m, chunk, a, s);
+    case KS_RELATIVE: return ks_tile_run_c1(OP, n, m, chunk, a, s);
+    case KS_SHIFT_REFLECTION: return ks_tile_run_c2(OP, n, m, chunk, a, s);
+    default: return ks_tile_run_c3(OP, n, m, chunk, a, s);
+  }
+}
+
 template <int OP>
 int dispatch(int cls, int n, int m, const KsEvalArgs& a, void* ws, size_t ws_bytes, void* stream, int from_basis = 0,
              int to_basis = 0, const double* tin = nullptr, double* tout = nullptr) {
@@ -143,6 +131,7 @@ int dispatch(int cls, int n, int m, const KsEvalArgs& a, void* ws, size_t ws_byt
   KsEvalArgs e = a;
   e.scratch = static_cast<double*>(ws);
   if constexpr (OP != ksg::KS_OP_TRANSFORM) {
+    if (use_tile(n, m)) return launch_tile<OP>(cls, n, m, e, s);
     if (use_warp32(n, m)) {
       switch (cls) {
         case KS_ORBIT: return launch_warp32<KS_ORBIT, OP>(e, s);
@@ -175,6 +164,10 @@ int ks_b200_abi_version(void) { return 1; }
 const char* ks_last_error(void) { return g_err; }
 
 void ks_debug_force_generic(int on) { g_force_generic = on != 0; }
+void ks_debug_tile(int enabled, int chunk_mb) {
+  g_tile_enabled = enabled != 0;
+  if (chunk_mb > 0) g_tile_chunk_mb = chunk_mb;
+}
 void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant == 3 || variant == 4) ? variant : 4; }
 
 int ks_mode_size(int cls, int n, int m) { return shape_ok(cls, n, m) ? (n - 1) * mode_cols(cls, m) : 0; }
@@ -184,6 +177,10 @@ size_t ks_workspace_bytes(int cls, int n, int m, int batch) {
   const int cols = mode_cols(cls, m);
   // generic path slots (always available: ks_transform uses it for every shape)
   size_t bytes = (size_t)generic_grid(batch) * ksg::slot_doubles(n, m, cols) * 8;
+  if (kst::size_ok(n) && kst::size_ok(m)) {
+    const size_t w = tile_workspace_bytes(n, m, cols, batch);
+    if (w > bytes) bytes = w;
+  }
   if (use_warp32(n, m)) {
     const size_t w = (size_t)warp32_grid(batch, 7) * ksw32::kMaxWarpsPerCta * 2 * 31 * cols * 8;
     if (w > bytes) bytes = w;

@@ -11,24 +11,19 @@
 // matvec :659-709, :2623-2660; rmatvec :711-755, :1984-2045, :3059-3115; costgrad :757-791; precondition :1034-1089.
 #pragma once
 #include "ks_common.cuh"
-#include "ks_warp32.cuh"  // Tup algebra
+#include "ks_pointwise.cuh"
 
 namespace ksg {
-using ksw32::Tup;
-using ksw32::dot_tup;
-using ksw32::dx_tup;
-using ksw32::rot_t;
-using ksw32::rot_x;
+using kspw::Geom;
+using kspw::Tup;
+using kspw::gload;
+using kspw::gproject;
+using kspw::gstore;
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 enum { KS_OP_TRANSFORM = 4 };
 
-struct Geom {
-  int n, m, h, k, cols, nm, nmax;
-  int log_n, log_m;  // -1 when not a power of two
-  double ct, cx;     // 1/sqrt(2n), 1/sqrt(2m)
-};
 struct GenArgs {
   KsEvalArgs e;
   Geom g;
@@ -46,55 +41,6 @@ KS_HD size_t slot_doubles(int n, int m, int cols) {
 KS_HD size_t smem_bytes(int n, int m) {
   const int nmax = n > m ? n : m;
   return (size_t)(n + m) * 16 + (size_t)kWarps * 2 * nmax * 16 + kWarps * 8 * 8;
-}
-
-template <int CLS>
-KS_DEVI bool has_a(int j) { return CLS == KS_ORBIT || CLS == KS_RELATIVE || (CLS == KS_SHIFT_REFLECTION && (j & 1)); }
-template <int CLS>
-KS_DEVI bool has_b(int j) {
-  return CLS == KS_ORBIT || CLS == KS_RELATIVE || CLS == KS_ANTISYMMETRIC || (CLS == KS_SHIFT_REFLECTION && !(j & 1));
-}
-template <int CLS>
-KS_DEVI Tup gload(const double* __restrict__ p, int j, int kp, const Geom& g) {
-  Tup t{0.0, 0.0, 0.0, 0.0};
-  if (CLS == KS_ORBIT || CLS == KS_RELATIVE) {
-    t.a1 = p[j * g.cols + kp];
-    t.b1 = p[j * g.cols + g.k + kp];
-    if (j > 0) {
-      t.a2 = p[(g.h + j) * g.cols + kp];
-      t.b2 = p[(g.h + j) * g.cols + g.k + kp];
-    }
-  } else if (has_a<CLS>(j)) {
-    t.a1 = p[j * g.cols + kp];
-    if (j > 0) t.a2 = p[(g.h + j) * g.cols + kp];
-  } else {
-    t.b1 = p[j * g.cols + kp];
-    if (j > 0) t.b2 = p[(g.h + j) * g.cols + kp];
-  }
-  return t;
-}
-template <int CLS>
-KS_DEVI void gstore(double* __restrict__ p, int j, int kp, const Geom& g, const Tup& t) {
-  if (CLS == KS_ORBIT || CLS == KS_RELATIVE) {
-    p[j * g.cols + kp] = t.a1;
-    p[j * g.cols + g.k + kp] = t.b1;
-    if (j > 0) {
-      p[(g.h + j) * g.cols + kp] = t.a2;
-      p[(g.h + j) * g.cols + g.k + kp] = t.b2;
-    }
-  } else if (has_a<CLS>(j)) {
-    p[j * g.cols + kp] = t.a1;
-    if (j > 0) p[(g.h + j) * g.cols + kp] = t.a2;
-  } else {
-    p[j * g.cols + kp] = t.b1;
-    if (j > 0) p[(g.h + j) * g.cols + kp] = t.b2;
-  }
-}
-template <int CLS>
-KS_DEVI void gproject(Tup& t, int j) {
-  if (!has_a<CLS>(j)) t.a1 = t.a2 = 0.0;
-  if (!has_b<CLS>(j)) t.b1 = t.b2 = 0.0;
-  if (j == 0) t.a2 = t.b2 = 0.0;
 }
 
 KS_DEVI double2 cmul(double2 a, double2 w) { return make_double2(fma(a.x, w.x, -a.y * w.y), fma(a.x, w.y, a.y * w.x)); }
@@ -253,7 +199,6 @@ KS_DEVI void pass_row(const Geom& g, double2* XC, double2* line, double2* tmp, c
 
 template <int CLS, int OP>
 __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) {
-  constexpr bool REL = (CLS == KS_RELATIVE);
   const KsEvalArgs& a = ga.e;
   const Geom g = ga.g;
   KS_DYN_SMEM(double2, smem);
@@ -279,7 +224,6 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
   double* FU = slot + 2 * (size_t)g.k * g.n;  // even offset: stays 16-byte aligned
   double* TU = FU + (size_t)g.n * g.m;
   const int n2 = g.n / 2;
-  const bool fix_t = a.cmask & KS_FIX_T, fix_x = a.cmask & KS_FIX_X, fix_s = (a.cmask & KS_FIX_S) || !REL;
 
   for (int orbit = blockIdx.x; orbit < a.batch; orbit += gridDim.x) {
     if constexpr (OP == KS_OP_TRANSFORM) {
@@ -324,28 +268,10 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
       __syncthreads();
       continue;
     } else {
-      const double* Mo = a.modes + (size_t)orbit * g.nm;
-      const int v_ld = a.v_ld ? a.v_ld : g.nm, out_ld = a.out_ld ? a.out_ld : g.nm;
-      const double* Vo = (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) ? a.vmodes + (size_t)orbit * v_ld : nullptr;
-      double* Oo = a.out_state + (size_t)orbit * out_ld;
-      double* Fo = (OP == KS_OP_COSTGRAD) ? (a.f_out ? a.f_out + (size_t)orbit * g.nm : TU) : Oo;
-      const double T = a.params[orbit * 3 + 0], Lx = a.params[orbit * 3 + 1], S = a.params[orbit * 3 + 2];
-      const double wbase = -1.0 * (ks::kTwoPi * g.n / T), qbase = ks::kTwoPi * g.m / Lx;
-      const double sig = REL ? S / T : 0.0;
-      const bool need_nuu = (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) || !fix_x;
-      double vt = 0.0, vx = 0.0, vs = 0.0;
-      if constexpr (OP == KS_OP_MATVEC) {
-        double v3[3];
-        for (int i = 0; i < 3; ++i) {
-          const int slot = ks::free_slot(a.cmask, i);
-          v3[i] = a.v_tail ? (slot < 0 ? 0.0 : Vo[g.nm + slot]) : a.vparams[orbit * 3 + i];
-        }
-        vt = fix_t ? 0.0 : v3[0] * (-1.0 / T);
-        vx = fix_x ? 0.0 : v3[1] * (1.0 / Lx);
-        vs = fix_s ? 0.0 : v3[2] * (-1.0 / T);
-      }
+      const kspw::OrbitCtx c = kspw::make_ctx<CLS, OP>(a, g, orbit, TU);
+      const bool need_nuu = kspw::need_nuu<OP>(a);
       // A: u modes -> XC
-      pass_col_inverse<CLS>(g, [&](int j, int kp) { return gload<CLS>(Mo, j, kp, g); }, XC, line, tmp, tw_n);
+      pass_col_inverse<CLS>(g, [&](int j, int kp) { return gload<CLS>(c.Mo, j, kp, g); }, XC, line, tmp, tw_n);
       __syncthreads();
       // B: XC -> field u (kept in FU); u^2 -> XC
       pass_row(g, XC, line, tmp, tw_m, true, need_nuu, [&](int t, int x, double2& v) {
@@ -355,77 +281,17 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
       });
       __syncthreads();
       // C: tuple stage 1 (+ fused second inverse)
-      double s_ff = 0.0, s_x = 0.0, s_d = 0.0, s_e = 0.0;
+      kspw::Sums sm;
       if (!need_nuu) {
         for (int i = threadIdx.x; i < g.k * g.n; i += kThreads) XC[i] = make_double2(0.0, 0.0);
         __syncthreads();
       }
       pass_col_forward<CLS>(g, XC, line, tmp, tw_n, [&](int j, int kp, Tup P, Tup& W) {
-        const double w = (j == 0) ? 0.0 : wbase * (j * (1.0 / g.n));
-        const double q = qbase * ((kp + 1) * (1.0 / g.m));
-        const double q2 = q * q, q4 = q2 * q2, d = q4 - q2, e = 2.0 * q2 - 4.0 * q4;
-        const double qn = 0.5 * q;
-        Tup N{-qn * P.b1, -qn * P.b2, qn * P.a1, qn * P.a2};
-        gproject<CLS>(N, j);
-        const Tup Mt = gload<CLS>(Mo, j, kp, g);
-        if constexpr (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) {
-          Tup F;
-          F.a1 = fma(d, Mt.a1, fma(-w, Mt.a2, N.a1));
-          F.a2 = fma(d, Mt.a2, fma(w, Mt.a1, N.a2));
-          F.b1 = fma(d, Mt.b1, fma(-w, Mt.b2, N.b1));
-          F.b2 = fma(d, Mt.b2, fma(w, Mt.b1, N.b2));
-          if constexpr (REL) {
-            const double sq = sig * q;
-            F.a1 = fma(sq, Mt.b1, F.a1);
-            F.a2 = fma(sq, Mt.b2, F.a2);
-            F.b1 = fma(-sq, Mt.a1, F.b1);
-            F.b2 = fma(-sq, Mt.a2, F.b2);
-          }
-          gproject<CLS>(F, j);
-          const double ff = dot_tup(F, F);
-          s_ff += ff;
-          gstore<CLS>(Fo, j, kp, g, F);
-          if constexpr (OP == KS_OP_COSTGRAD) {
-            const double mf = dot_tup(Mt, F), xt = w * rot_t(Mt, F);
-            s_e += fma(e + d, mf, xt - ff);
-            s_x += xt;
-            if constexpr (REL) s_d += q * rot_x(Mt, F);
-            W = dx_tup(F, q);
-          }
-        } else if constexpr (OP == KS_OP_RMATVEC) {
-          const Tup V = gload<CLS>(Vo, j, kp, g);
-          const double dd = REL ? q * rot_x(Mt, V) : 0.0;
-          s_e += fma(e, dot_tup(Mt, V), fma(sig, dd, -dot_tup(N, V)));
-          s_x += w * rot_t(Mt, V);
-          s_d += dd;
-          W = dx_tup(V, q);
-        } else {
-          const Tup V = gload<CLS>(Vo, j, kp, g);
-          const double cdx = REL ? (-sig * vt + sig * vx + vs) * q : 0.0, cdt = vt * w, ce = vx * e;
-          Tup R;
-          R.a1 = fma(d, V.a1, -w * V.a2);
-          R.a2 = fma(d, V.a2, w * V.a1);
-          R.b1 = fma(d, V.b1, -w * V.b2);
-          R.b2 = fma(d, V.b2, w * V.b1);
-          if constexpr (REL) {
-            const double sq = sig * q;
-            R.a1 = fma(sq, V.b1, R.a1);
-            R.a2 = fma(sq, V.b2, R.a2);
-            R.b1 = fma(-sq, V.a1, R.b1);
-            R.b2 = fma(-sq, V.a2, R.b2);
-          }
-          R.a1 += fma(ce, Mt.a1, fma(-cdt, Mt.a2, fma(-cdx, Mt.b1, -vx * N.a1)));
-          R.a2 += fma(ce, Mt.a2, fma(cdt, Mt.a1, fma(-cdx, Mt.b2, -vx * N.a2)));
-          R.b1 += fma(ce, Mt.b1, fma(-cdt, Mt.b2, fma(cdx, Mt.a1, -vx * N.b1)));
-          R.b2 += fma(ce, Mt.b2, fma(cdt, Mt.b1, fma(cdx, Mt.a2, -vx * N.b2)));
-          gproject<CLS>(R, j);
-          gstore<CLS>(Fo, j, kp, g, R);
-          W = V;
-        }
+        kspw::stage1_point<CLS, OP>(c, g, j, kp, P, W, sm);
       }, OP != KS_OP_EQN);
       // deterministic CTA reduction of the scalar sums
       {
-        const double r0 = warp_sum(s_ff), r1 = warp_sum(s_e), r2 = warp_sum(fma(-sig, s_d, s_x)), r3 = warp_sum(s_d);
+        const double r0 = warp_sum(sm.ff), r1 = warp_sum(sm.e), r2 = warp_sum(fma(-c.sig, sm.d, sm.x)), r3 = warp_sum(sm.d);
         if (lane == 0) {
           red[warp * 8 + 0] = r0;
           red[warp * 8 + 1] = r1;
@@ -441,25 +307,7 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
             t2 += red[wq * 8 + 2];
             t3 += red[wq * 8 + 3];
           }
-          if ((OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) && a.out_cost) a.out_cost[orbit] = 0.5 * t0;
-          if ((OP == KS_OP_COSTGRAD || OP == KS_OP_RMATVEC) && (a.out_params || a.out_tail)) {
-            double gt = fix_t ? 0.0 : (-1.0 / T) * t2, gx = fix_x ? 0.0 : (1.0 / Lx) * t1, gs = fix_s ? 0.0 : (-1.0 / T) * t3;
-            if (OP == KS_OP_COSTGRAD && a.precond) {
-              if (!fix_t) gt *= 1.0 / T;
-              if (!fix_x) gx *= 1.0 / ((Lx * Lx) * (Lx * Lx));
-            }
-            if (a.out_tail) {
-              const double g3[3] = {gt, gx, gs};
-              for (int i = 0; i < 3; ++i) {
-                const int slot = ks::free_slot(a.cmask, i);
-                if (slot >= 0) Oo[g.nm + slot] = g3[i];
-              }
-            } else {
-              a.out_params[orbit * 3 + 0] = gt;
-              a.out_params[orbit * 3 + 1] = gx;
-              a.out_params[orbit * 3 + 2] = gs;
-            }
-          }
+          kspw::finish_scalars<CLS, OP>(a, g, c, orbit, t0, t1, t2, t3);
         }
       }
       __syncthreads();
@@ -471,33 +319,7 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
       __syncthreads();
       // E: tuple stage 2
       pass_col_forward<CLS>(g, XC, line, tmp, tw_n, [&](int j, int kp, Tup P, Tup&) {
-        const double w = (j == 0) ? 0.0 : wbase * (j * (1.0 / g.n));
-        const double q = qbase * ((kp + 1) * (1.0 / g.m));
-        const double q2 = q * q, q4 = q2 * q2, d = q4 - q2;
-        Tup R;
-        if constexpr (OP == KS_OP_MATVEC) {
-          const Tup A0 = gload<CLS>(Fo, j, kp, g);
-          R = Tup{fma(-q, P.b1, A0.a1), fma(-q, P.b2, A0.a2), fma(q, P.a1, A0.b1), fma(q, P.a2, A0.b2)};
-        } else {
-          const Tup V = (OP == KS_OP_COSTGRAD) ? gload<CLS>(Fo, j, kp, g) : gload<CLS>(Vo, j, kp, g);
-          R.a1 = fma(d, V.a1, fma(w, V.a2, -P.a1));
-          R.a2 = fma(d, V.a2, fma(-w, V.a1, -P.a2));
-          R.b1 = fma(d, V.b1, fma(w, V.b2, -P.b1));
-          R.b2 = fma(d, V.b2, fma(-w, V.b1, -P.b2));
-          if constexpr (REL) {
-            const double sq = sig * q;
-            R.a1 = fma(-sq, V.b1, R.a1);
-            R.a2 = fma(-sq, V.b2, R.a2);
-            R.b1 = fma(sq, V.a1, R.b1);
-            R.b2 = fma(sq, V.a2, R.b2);
-          }
-          if (OP == KS_OP_COSTGRAD && a.precond) {
-            const double pm = 1.0 / ((w < 0 ? -w : w) + q2 + q4);
-            R.a1 *= pm; R.a2 *= pm; R.b1 *= pm; R.b2 *= pm;
-          }
-        }
-        gproject<CLS>(R, j);
-        gstore<CLS>(Oo, j, kp, g, R);
+        kspw::stage2_point<CLS, OP>(c, g, j, kp, P);
       }, false);
       __syncthreads();
     }

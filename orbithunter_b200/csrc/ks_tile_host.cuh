@@ -1,0 +1,145 @@
+// Launch code of the tile path for ONE symmetry class (KS_TILE_CLS), included by ks_tile_c{0..3}.cu so the four classes
+// compile in parallel.  Everything here has internal linkage except ks_tile_run_c<CLS>.
+#pragma once
+#include <cstring>
+
+#include "ks_host.cuh"
+#include "ks_tile.cuh"
+
+#ifndef KS_TILE_CLS
+#error "define KS_TILE_CLS (0..3) before including ks_tile_host.cuh"
+#endif
+
+namespace {
+using namespace ksh;
+constexpr int kCls = KS_TILE_CLS;
+template <class K>
+int tile_ctas_per_sm(K kern, size_t smem) {
+#ifdef KS_HOST_EMUL
+  (void)kern; (void)smem;
+  return 2;
+#else
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kst::kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+  return nb;
+#endif
+}
+template <class K>
+int tile_launch(K kern, size_t smem, int ntiles, const kst::TileArgs& ta, cudaStream_t s) {
+  static int per_sm = 0;  // one static per kernel instantiation
+  if (!per_sm) per_sm = tile_ctas_per_sm(kern, smem);
+  const int cap = sm_count() * per_sm;
+  KS_LAUNCH(kern, ntiles < cap ? ntiles : cap, kst::kThreads, smem, s, ta);
+  return 0;
+}
+int tile_ensure_twiddles(cudaStream_t s) {
+#ifdef KS_HOST_EMUL
+  static bool done = false;
+  if (!done) { KS_LAUNCH(kst::tw_init_kernel, 2, 256, 0, s, 0); done = true; }
+#else
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(KS_ERR_LAUNCH, "cudaGetDevice failed");
+  if (!done[dev]) {
+    KS_LAUNCH(kst::tw_init_kernel, 2, 256, 0, s, 0);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return fail(KS_ERR_LAUNCH, "twiddle table kernel failed");
+    done[dev] = true;
+  }
+#endif
+  return 0;
+}
+template <int CLS, int N>
+int tile_colinv(const kst::TileArgs& ta, cudaStream_t s) {
+  return tile_launch(kst::tile_colinv_kernel<CLS, N>, kst::tile_smem_bytes<N>(), ta.e.batch * ta.nkb, ta, s);
+}
+template <int CLS, int OP, int N, int STAGE>
+int tile_colfwd(const kst::TileArgs& ta, cudaStream_t s) {
+  return tile_launch(kst::tile_colfwd_kernel<CLS, OP, N, STAGE>, kst::tile_smem_bytes<N>(), ta.e.batch * ta.nkb, ta, s);
+}
+template <int MODE>
+int tile_row(const kst::TileArgs& ta, cudaStream_t s) {
+  const int nt = ta.e.batch * ta.ntb;
+  switch (ta.g.m) {
+    case 64: return tile_launch(kst::tile_row_kernel<64, MODE>, kst::tile_smem_bytes<64>(), nt, ta, s);
+    case 128: return tile_launch(kst::tile_row_kernel<128, MODE>, kst::tile_smem_bytes<128>(), nt, ta, s);
+    default: return tile_launch(kst::tile_row_kernel<256, MODE>, kst::tile_smem_bytes<256>(), nt, ta, s);
+  }
+}
+template <int CLS, int OP, int N>
+int tile_chunk_run(kst::TileArgs& ta, cudaStream_t s) {
+  const bool nuu = (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) || !(ta.e.cmask & KS_FIX_X);
+  tile_colinv<CLS, N>(ta, s);
+  ta.forward = nuu ? 1 : 0;
+  ta.zero_nuu = nuu ? 0 : 1;
+  tile_row<kst::MODE_SQ>(ta, s);
+  tile_colfwd<CLS, OP, N, 1>(ta, s);
+  if constexpr (OP != KS_OP_MATVEC) {
+    KS_LAUNCH((kst::tile_finalize_kernel<CLS, OP>), (ta.e.batch + 127) / 128, 128, 0, s, ta);
+  }
+  if constexpr (OP != KS_OP_EQN) {
+    ta.forward = 1;
+    tile_row<kst::MODE_MUL>(ta, s);
+    tile_colfwd<CLS, OP, N, 2>(ta, s);
+  }
+  return 0;
+}
+template <int CLS, int OP>
+int launch_tile(int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s) {
+  if (int rc = tile_ensure_twiddles(s)) return rc;
+  const kspw::Geom g = make_geom(CLS, n, m);
+  const int KB = kst::col_lines(n), TB = kst::col_lines(m);
+  const int nkb = (g.k + KB - 1) / KB, ntb = (n / 2) / TB;
+  char* base = reinterpret_cast<char*>(a.scratch);
+  auto take = [&](size_t doubles) {
+    char* p = base;
+    base += (doubles * 8 + 255) & ~(size_t)255;
+    return reinterpret_cast<double*>(p);
+  };
+  kst::TileArgs ta;
+  std::memset(&ta, 0, sizeof(ta));
+  ta.g = g;
+  ta.XC = reinterpret_cast<double2*>(take((size_t)chunk * g.k * n * 2));
+  ta.FU2 = reinterpret_cast<double2*>(take((size_t)chunk * n * m));
+  ta.TU = take((size_t)chunk * g.nm);
+  ta.partial = take((size_t)chunk * nkb * 4);
+  ta.nkb = nkb;
+  ta.ntb = ntb;
+  const size_t v_ld = a.v_ld ? a.v_ld : g.nm, out_ld = a.out_ld ? a.out_ld : g.nm;
+  for (int b0 = 0; b0 < a.batch; b0 += chunk) {
+    KsEvalArgs e = a;
+    e.batch = a.batch - b0 < chunk ? a.batch - b0 : chunk;
+    e.modes += (size_t)b0 * g.nm;
+    e.params += (size_t)b0 * 3;
+    if (e.vmodes) e.vmodes += (size_t)b0 * v_ld;
+    if (e.vparams) e.vparams += (size_t)b0 * 3;
+    if (e.out_state) e.out_state += (size_t)b0 * out_ld;
+    if (e.out_params) e.out_params += (size_t)b0 * 3;
+    if (e.out_cost) e.out_cost += b0;
+    if (e.f_out) e.f_out += (size_t)b0 * g.nm;
+    ta.e = e;
+    switch (n) {
+      case 64: tile_chunk_run<CLS, OP, 64>(ta, s); break;
+      case 128: tile_chunk_run<CLS, OP, 128>(ta, s); break;
+      default: tile_chunk_run<CLS, OP, 256>(ta, s); break;
+    }
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "tile kernel launch failed");
+}
+
+
+int tile_run(int op, int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s) {
+  switch (op) {
+    case KS_OP_EQN: return launch_tile<kCls, KS_OP_EQN>(n, m, chunk, a, s);
+    case KS_OP_COSTGRAD: return launch_tile<kCls, KS_OP_COSTGRAD>(n, m, chunk, a, s);
+    case KS_OP_MATVEC: return launch_tile<kCls, KS_OP_MATVEC>(n, m, chunk, a, s);
+    case KS_OP_RMATVEC: return launch_tile<kCls, KS_OP_RMATVEC>(n, m, chunk, a, s);
+    default: return fail(KS_ERR_ARG, "tile path: unknown op");
+  }
+}
+}  // namespace
+
+#define KS_TILE_CAT_(a, b) a##b
+#define KS_TILE_CAT(a, b) KS_TILE_CAT_(a, b)
+int KS_TILE_CAT(ks_tile_run_c, KS_TILE_CLS)(int op, int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s) {
+  return tile_run(op, n, m, chunk, a, s);
+}

@@ -31,11 +31,19 @@ def needs_build():
 def build(force=False):
     if not force and not needs_build():
         return OUT
-    cmd = ["g++", "-std=c++20", "-O1", "-mfma", "-fPIC", "-shared", "-pthread", "-DKS_HOST_EMUL", "-Wno-attributes",
-           "-I", HERE, "-I", CSRC, "-o", OUT]
-    for s in sources():
-        cmd += ["-x", "c++", s]
-    subprocess.check_call(cmd)
+    flags = ["-std=c++20", "-O1", "-mfma", "-fPIC", "-pthread", "-DKS_HOST_EMUL", "-Wno-attributes", "-I", HERE, "-I", CSRC]
+    objdir = os.path.join(HERE, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    objs, procs = [], []
+    for s in sources():  # one g++ per translation unit, all at once
+        obj = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
+        cmd = ["g++", *flags, "-c", "-x", "c++", s, "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd)))
+        objs.append(obj)
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    subprocess.check_call(["g++", "-shared", "-pthread", "-o", OUT, *objs])
     return OUT
 
 

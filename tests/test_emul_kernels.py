@@ -72,6 +72,21 @@ def test_generic_kernel_all_ops(cid, shape):
         E.lib().ks_debug_force_generic(0)
 
 
+@pytest.mark.parametrize("cid,shape", [(0, (64, 64)), (1, (64, 64)), (2, (64, 64)), (3, (64, 64)), (1, (128, 64)), (2, (64, 128)),
+                                       (0, (64, 256)), (3, (256, 64))])
+def test_tile_kernels_all_ops(cid, shape):
+    """Large-grid multi-pass path (ks_tile.cuh): every pass kernel, every radix plan (64 = 8x8, 128 = 16x8, 256 = 16x16)."""
+    L = E.lib()
+    L.ks_debug_force_generic(0)
+    L.ks_debug_tile(1, 1 if shape == (64, 64) else 64)  # 1 MB budget: the 3-orbit batch runs as several chunks
+    try:
+        cons_list = (ko.default_constraints(cid), (True, True, True)) if shape == (64, 64) else (ko.default_constraints(cid),)
+        for cons in cons_list:
+            _check_all_ops(cid, shape[0], shape[1], 3, cons)
+    finally:
+        L.ks_debug_tile(1, 64)
+
+
 @pytest.mark.parametrize("cid", range(4))
 def test_transforms_all_bases(cid):
     for (n, m) in ((32, 32), (10, 12)):

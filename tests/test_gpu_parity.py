@@ -158,6 +158,39 @@ def test_warp32_matches_generic_kernel(cid):
 
 
 @pytest.mark.parametrize("cid", range(4))
+@pytest.mark.parametrize("shape,B", [((64, 64), 97), ((128, 64), 9), ((64, 256), 5), ((256, 256), 3)])
+def test_tile_matches_generic_kernel(cid, shape, B):
+    """The multi-pass large-grid path (ks_tile.cuh) against the generic-size kernel, incl. a batch split into chunks."""
+    from orbithunter_b200 import _lib
+
+    n, m = shape
+    rng = np.random.RandomState(n + m + cid)
+    M = np.stack([ko.populate_state(60.0, 44.0, n, m, s, cid) for s in range(B)])
+    p = np.stack([60.0 + rng.rand(B), 44.0 + rng.rand(B), (rng.randn(B) if cid == 1 else np.zeros(B))], axis=1)
+    u, vb = _b(cid, M, p), _b(cid, rng.randn(*M.shape), rng.randn(B, 3))
+    L = _lib.lib()
+
+    def run():
+        c, g, F = u.costgrad(preconditioning=True, return_eqn=True)
+        r = u.rmatvec(vb)
+        return [c.cpu().numpy(), g.cpu_state(), g.cpu_parameters(), F.cpu_state(), u.matvec(vb).cpu_state(), r.cpu_state(),
+                r.cpu_parameters(), u.eqn().cpu_state()]
+
+    try:
+        L.ks_debug_tile(1, 2)  # 2 MB workspace budget: 1 .. 20 orbits per chunk
+        small = run()
+        L.ks_debug_tile(1, 64)
+        big = run()
+        L.ks_debug_tile(0, 0)
+        ref = run()
+    finally:
+        L.ks_debug_tile(1, 64)
+    for x, y, z in zip(small, big, ref):
+        assert np.array_equal(x, y)  # chunking does not change a single bit
+        assert relerr(x, z) < _tol(M[0], cid, 44.0)
+
+
+@pytest.mark.parametrize("cid", range(4))
 def test_properties_at_full_batch(cid):
     """BASELINE config 2/3 sizes: adjoint identity <Jv,w> = <v,J^T w> + params, transform round trip, determinism."""
     n, m, B = (32, 32, 4096) if cid == 0 else (64, 64, 512)
