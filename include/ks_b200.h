@@ -42,6 +42,10 @@ void ks_debug_warp32_variant(int variant);
 /* tuning hook, large-grid (n, m in {64, 128, 256}) tile path: enabled = 0 routes those shapes through the generic
  * kernel (cross-check); chunk_mb > 0 sets the workspace budget that bounds how many orbits one pass sequence covers. */
 void ks_debug_tile(int enabled, int chunk_mb);
+/* test hook, GMRES step kernel: 1 (default) = thread-block cluster per orbit (1/2/4/8 CTAs by vector length), vector
+ * slices in registers; 2/4/8 = at least that many CTAs per orbit; 0 = one CTA per orbit, vectors in HBM (cross-check;
+ * also used automatically when N > 65536). */
+void ks_debug_gmres_cluster(int mode);
 
 /* rows*cols of the modes basis for (cls, n, m); 0 if the shape is not supported. */
 int ks_mode_size(int cls, int n, int m);

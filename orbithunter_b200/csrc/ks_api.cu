@@ -96,8 +96,9 @@ int launch_generic(const ksg::GenArgs& ga, cudaStream_t s) {
 
 // ---- tile path (n, m in {64, 128, 256}): kernels and launch code live in ks_tile_c{0..3}.cu (one class per translation
 // unit, compiled in parallel); see ks_tile_host.cuh ----
+int g_gmres_cluster = 1;  // 0 = one CTA per orbit GMRES step (cross-check), 1 = auto cluster size, 2/4/8 = at least that size
 bool g_tile_enabled = true;
-int g_tile_chunk_mb = 64;
+int g_tile_chunk_mb = 256;
 bool use_tile(int n, int m) { return g_tile_enabled && !g_force_generic && kst::size_ok(n) && kst::size_ok(m); }
 int tile_chunk(int n, int m, int cols, int batch) {
   const size_t per = kst::orbit_doubles(n, m, cols) * 8;
@@ -164,6 +165,7 @@ int ks_b200_abi_version(void) { return 1; }
 const char* ks_last_error(void) { return g_err; }
 
 void ks_debug_force_generic(int on) { g_force_generic = on != 0; }
+void ks_debug_gmres_cluster(int mode) { g_gmres_cluster = (mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8) ? mode : 1; }
 void ks_debug_tile(int enabled, int chunk_mb) {
   g_tile_enabled = enabled != 0;
   if (chunk_mb > 0) g_tile_chunk_mb = chunk_mb;
@@ -695,6 +697,14 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
       g.B = batch; g.N = N; g.R = restart; g.maxiter = inner_maxiter; g.n = n; g.m = m; g.cols = mode_cols(cls, m);
       g.precond = preconditioning; g.cmask = cmask; g.rtol = rtol; g.atol_in = atol;
       KS_LAUNCH(kskry::gmres_start_kernel, batch, kskry::kThreads, 0, s, g);
+      // GMRES step: vectors longer than 8192 are split over a cluster of 2 / 4 / 8 CTAs per orbit, each holding its slice
+      // in registers; shorter ones (and N > 65536, and the debug switch) use the one-CTA-per-orbit kernel
+      int gm_cluster = 0;
+      if (g_gmres_cluster > 1 || (g_gmres_cluster == 1 && N > kskry::kSlice)) {  // short vectors: one CTA per orbit is faster
+        gm_cluster = g_gmres_cluster;
+        while (gm_cluster < kskry::kMaxCluster && (size_t)gm_cluster * kskry::kSlice < (size_t)N) gm_cluster *= 2;
+        if ((size_t)gm_cluster * kskry::kSlice < (size_t)N) gm_cluster = 0;
+      }
       const long max_steps = (long)inner_maxiter * (restart + 1) + 2;
       for (long st = 0; st < max_steps; ++st) {
         if (st % check_every == 0) {
@@ -705,7 +715,13 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
         if ((rc = op_matvec(vin, Fy)) != 0) return rc;
         if ((rc = op_rmatvec(Fy, wout)) != 0) return rc;
         cudaMemsetAsync(counters, 0, 4, s);
-        KS_LAUNCH(kskry::gmres_step_kernel, batch, kskry::kThreads, 0, s, g);
+        if (gm_cluster > 0) {
+          if (KS_LAUNCH_CLUSTER(kskry::gmres_step_cluster_kernel, (unsigned)batch * gm_cluster, (unsigned)kskry::kThreads,
+                                (unsigned)gm_cluster, (size_t)kskry::kClusterSmemBytes, s, g) != cudaSuccess)
+            return fail(KS_ERR_LAUNCH, "newton-krylov: cluster launch of the GMRES step failed");
+        } else {
+          KS_LAUNCH(kskry::gmres_step_kernel, batch, kskry::kThreads, 0, s, g);
+        }
         ++n_steps;
       }
     } else {

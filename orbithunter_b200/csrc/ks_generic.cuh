@@ -287,7 +287,9 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
         __syncthreads();
       }
       pass_col_forward<CLS>(g, XC, line, tmp, tw_n, [&](int j, int kp, Tup P, Tup& W) {
-        kspw::stage1_point<CLS, OP>(c, g, j, kp, P, W, sm);
+        Tup Mt, V{0.0, 0.0, 0.0, 0.0};
+        kspw::stage1_loads<CLS, OP>(c, g, j, kp, Mt, V);
+        kspw::stage1_point<CLS, OP>(c, g, j, kp, P, Mt, V, W, sm);
       }, OP != KS_OP_EQN);
       // deterministic CTA reduction of the scalar sums
       {
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(kThreads) ks_generic_kernel(const GenArgs ga) 
       __syncthreads();
       // E: tuple stage 2
       pass_col_forward<CLS>(g, XC, line, tmp, tw_n, [&](int j, int kp, Tup P, Tup&) {
-        kspw::stage2_point<CLS, OP>(c, g, j, kp, P);
+        kspw::stage2_point<CLS, OP>(c, g, j, kp, P, kspw::stage2_load<CLS, OP>(c, g, j, kp));
       }, false);
       __syncthreads();
     }

@@ -305,6 +305,266 @@ __global__ void __launch_bounds__(kThreads) gmres_step_kernel(const GmresState g
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// GMRES step, thread-block-cluster version: the C CTAs of one cluster share ONE orbit, each owning a slice of at most
+// kSlice elements of every length-N vector.  The vector being orthogonalised stays in registers for the whole modified
+// Gram-Schmidt sweep (the basis is the only HBM traffic, read exactly once, next vector prefetched during the
+// reduction), dot products are block sums combined across the cluster through distributed shared memory in rank order
+// (deterministic), and rank 0 runs the small Hessenberg / Givens update.  Same recurrences as gmres_step_kernel.
+// All shared memory is dynamic (the CPU emulation runs the blocks of a cluster concurrently).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSliceRegs = 32;
+constexpr int kSlice = kThreads * kSliceRegs;  // 8192 elements per CTA
+constexpr int kMaxCluster = 8;
+constexpr int kClusterSmemBytes = (kThreads / 32 + 2 * 2 + 2) * 8 + 16;
+
+struct ClusterRed {
+  double* sh;     // [kThreads/32]
+  double* part;   // [2]  this block's partial, alternating slots
+  double* bc;     // [2]  block-wide broadcast of the cluster total / of rank 0's flag
+  int phase;
+  unsigned C, rank;
+};
+// sum over the whole cluster; every thread of every block gets the same value
+KS_DEVI double cluster_sum(double v, ClusterRed& cr) {
+  const double t = block_sum(v, cr.sh);
+  if (cr.C == 1) return t;
+  if (threadIdx.x == 0) cr.part[cr.phase] = t;
+  ks_cluster_sync();
+  if (threadIdx.x < 32) {
+    double r = threadIdx.x < cr.C ? *ks_cluster_map(cr.part + cr.phase, threadIdx.x) : 0.0;
+    double tot = 0.0;
+    for (unsigned k = 0; k < cr.C; ++k) tot += __shfl_sync(0xffffffffu, r, (int)k);  // rank order
+    if (threadIdx.x == 0) cr.bc[0] = tot;
+  }
+  __syncthreads();
+  const double tot = cr.bc[0];
+  __syncthreads();
+  cr.phase ^= 1;
+  return tot;
+}
+
+__global__ void __launch_bounds__(kThreads) gmres_step_cluster_kernel(const GmresState g) {
+  KS_DYN_SMEM(double, dsm);
+  ClusterRed cr;
+  cr.sh = dsm;
+  cr.part = dsm + kThreads / 32;
+  cr.bc = cr.part + 2;
+  double* flag = cr.bc + 2;  // [2] rank 0: end_cycle / done, read by the other ranks through DSMEM
+  cr.phase = 0;
+  cr.C = ks_cluster_size();
+  cr.rank = ks_cluster_rank();
+  const int b = blockIdx.x / cr.C;
+  int* ic = g.ic + b * IC_COUNT;
+  const int state = ic[IC_STATE];
+  if (state == ST_DONE) return;  // uniform over the cluster
+  ks_cluster_sync();             // every block has read the state before rank 0 may change it
+  const bool lead = cr.rank == 0 && threadIdx.x == 0;
+  double* sc = g.sc + b * SC_COUNT;
+  const Diag dg = make_diag(g.n, g.m, g.cols, g.cmask, g.params[b * 3 + 0], g.params[b * 3 + 1]);
+  double* V = g.V + (size_t)b * (g.R + 1) * g.N;
+  double* H = g.H + (size_t)b * g.R * (g.R + 1);
+  double* Gv = g.G + (size_t)b * g.R * 2;
+  double* S = g.S + (size_t)b * (g.R + 1);
+  double* x = g.x + (size_t)b * g.N;
+  double* vin = g.vin + (size_t)b * g.N;
+  const double* ww = g.w + (size_t)b * g.N;
+  // this block's slice: elements lo + threadIdx.x + kThreads * r, r < kSliceRegs
+  const int per = (g.N + (int)cr.C - 1) / (int)cr.C;
+  const int lo = (int)cr.rank * per, hi = (lo + per < g.N) ? lo + per : g.N;
+  const int i0 = lo + (int)threadIdx.x;
+  auto rank0_flag = [&](int slot) -> bool {  // after a cluster sync: rank 0's flag[slot], same value in every thread
+    if (threadIdx.x == 0) cr.bc[1] = *ks_cluster_map(flag + slot, 0);
+    __syncthreads();
+    const bool f = cr.bc[1] != 0.0;
+    __syncthreads();
+    return f;
+  };
+  auto begin_cycle = [&](bool r_is_b) {  // gmres_begin_cycle on slices                       (iterative.py:741-748)
+    const double* bb = g.b + (size_t)b * g.N;
+    double r[kSliceRegs];
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < kSliceRegs; ++q) {
+      const int i = i0 + q * kThreads;
+      r[q] = 0.0;
+      if (i < hi) {
+        r[q] = r_is_b ? bb[i] : bb[i] - ww[i];
+        if (g.precond) r[q] *= dg.at(i);
+      }
+      acc += r[q] * r[q];
+    }
+    const double tmp = sqrt(cluster_sum(acc, cr));
+    const double inv = 1.0 / tmp;
+#pragma unroll
+    for (int q = 0; q < kSliceRegs; ++q) {
+      const int i = i0 + q * kThreads;
+      if (i < hi) {
+        const double v = r[q] * inv;
+        V[i] = v;
+        vin[i] = v;
+      }
+    }
+    if (lead) {
+      for (int i = 0; i <= g.R; ++i) S[i] = 0.0;
+      S[0] = tmp;
+      ic[IC_COL] = 0;
+      ic[IC_BREAK] = 0;
+      ic[IC_STATE] = ST_ARNOLDI;
+    }
+  };
+  if (state == ST_ARNOLDI) {
+    const int col = ic[IC_COL];
+    double w[kSliceRegs], vc[kSliceRegs], vn[kSliceRegs];
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < kSliceRegs; ++q) {
+      const int i = i0 + q * kThreads;
+      w[q] = 0.0;
+      vc[q] = 0.0;
+      if (i < hi) {
+        w[q] = g.precond ? ww[i] * dg.at(i) : ww[i];
+        vc[q] = V[i];
+      }
+      acc += w[q] * w[q];
+    }
+    const double h0 = sqrt(cluster_sum(acc, cr));
+    for (int k = 0; k <= col; ++k) {                                                      // modified Gram-Schmidt (:767-772)
+      if (k < col) {
+        const double* vk1 = V + (size_t)(k + 1) * g.N;
+#pragma unroll
+        for (int q = 0; q < kSliceRegs; ++q) {
+          const int i = i0 + q * kThreads;
+          vn[q] = i < hi ? vk1[i] : 0.0;
+        }
+      }
+      double d = 0.0;
+#pragma unroll
+      for (int q = 0; q < kSliceRegs; ++q) d += vc[q] * w[q];
+      d = cluster_sum(d, cr);
+      if (lead) H[col * (g.R + 1) + k] = d;
+#pragma unroll
+      for (int q = 0; q < kSliceRegs; ++q) {
+        w[q] -= d * vc[q];
+        vc[q] = vn[q];
+      }
+    }
+    acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < kSliceRegs; ++q) acc += w[q] * w[q];
+    const double h1 = sqrt(cluster_sum(acc, cr));
+    const bool breakdown = h1 <= kEps * h0;                                               // (:777-781)
+    double* wv = V + (size_t)(col + 1) * g.N;
+    {
+      const double inv = breakdown ? 1.0 : 1.0 / h1;
+#pragma unroll
+      for (int q = 0; q < kSliceRegs; ++q) {
+        const int i = i0 + q * kThreads;
+        w[q] *= inv;
+        if (i < hi) wv[i] = w[q];
+      }
+    }
+    if (lead) {
+      double* hc = H + col * (g.R + 1);
+      hc[col + 1] = breakdown ? 0.0 : h1;
+      for (int k = 0; k < col; ++k) {                                                     // past rotations (:784-787)
+        const double c = Gv[2 * k], s = Gv[2 * k + 1], n0 = hc[k], n1 = hc[k + 1];
+        hc[k] = c * n0 + s * n1;
+        hc[k + 1] = -s * n0 + c * n1;
+      }
+      double c, s, mag;
+      lartg(hc[col], hc[col + 1], c, s, mag);                                             // (:790-792)
+      Gv[2 * col] = c;
+      Gv[2 * col + 1] = s;
+      hc[col] = mag;
+      hc[col + 1] = 0.0;
+      const double tmp = -s * S[col];
+      S[col] = c * S[col];
+      S[col + 1] = tmp;
+      const double presid = tmp < 0 ? -tmp : tmp;
+      sc[SC_PRESID] = presid;
+      ic[IC_INNER] += 1;
+      ic[IC_BREAK] = breakdown ? 1 : 0;
+      const bool end_cycle = (presid <= sc[SC_PTOL]) || breakdown || (col + 1 == g.R);    // (:805, loop bound)
+      flag[0] = end_cycle ? 1.0 : 0.0;
+      if (end_cycle) {
+        if (hc[col] == 0.0) S[col] = 0.0;                                                 // (:812-824); y overwrites S
+        for (int k = col; k > 0; --k) {
+          if (S[k] != 0.0) {
+            S[k] /= H[k * (g.R + 1) + k];
+            const double t = S[k];
+            for (int i = 0; i < k; ++i) S[i] -= t * H[k * (g.R + 1) + i];
+          }
+        }
+        if (S[0] != 0.0) S[0] /= H[0];
+        ic[IC_STATE] = ST_RESID;
+      } else {
+        ic[IC_COL] = col + 1;
+      }
+      __threadfence();
+    }
+    ks_cluster_sync();  // rank 0's flag (shared memory) and S (global) are visible to the whole cluster
+    if (rank0_flag(0)) {
+#pragma unroll 4
+      for (int q = 0; q < kSliceRegs; ++q) {                                              // x += y @ v[:col+1]  (:826)
+        const int i = i0 + q * kThreads;
+        if (i < hi) {
+          double xi = x[i];
+          for (int k = 0; k <= col; ++k) xi += S[k] * V[(size_t)k * g.N + i];
+          x[i] = xi;
+          vin[i] = xi;                                                                    // next: r = b - A x
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kSliceRegs; ++q) {
+        const int i = i0 + q * kThreads;
+        if (i < hi) vin[i] = w[q];
+      }
+    }
+    if (lead) atomicAdd(g.n_active, 1);
+  } else {  // ST_RESID: w = A x                                                            (:828-851)
+    const double* bb = g.b + (size_t)b * g.N;
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < kSliceRegs; ++q) {
+      const int i = i0 + q * kThreads;
+      const double r = i < hi ? bb[i] - ww[i] : 0.0;
+      acc += r * r;
+    }
+    const double rnorm = sqrt(cluster_sum(acc, cr));
+    if (lead) {
+      sc[SC_RNORM] = rnorm;
+      const int iter = ic[IC_ITER] + 1;
+      ic[IC_ITER] = iter;
+      const double atol = sc[SC_ATOL], presid = sc[SC_PRESID];
+      int done = 0;
+      if (rnorm <= atol) {
+        done = 1;
+      } else if (ic[IC_BREAK]) {
+        done = 1;
+      } else {
+        double f = sc[SC_PFAC];
+        f = (presid <= sc[SC_PTOL]) ? fmax(kEps, 0.25 * f) : fmin(1.0, 1.5 * f);
+        sc[SC_PFAC] = f;
+        sc[SC_PTOL] = presid * fmin(f, atol / rnorm);
+        if (iter >= g.maxiter) done = 1;
+      }
+      if (done) {
+        ic[IC_INFO] = (rnorm <= atol) ? 0 : g.maxiter;
+        ic[IC_STATE] = ST_DONE;
+      }
+      flag[1] = done ? 1.0 : 0.0;
+    }
+    ks_cluster_sync();
+    if (!rank0_flag(1)) {
+      begin_cycle(false);
+      if (lead) atomicAdd(g.n_active, 1);
+    }
+  }
+  ks_cluster_sync();  // no block may exit while a peer can still read its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // LSQR (SciPy _isolve/lsqr.py, damp = 0, x0 = None).  Phases: 0 = waiting for A v, 1 = waiting for A^T u.
 // ---------------------------------------------------------------------------------------------------------------
 enum { LQ_ALFA = 0, LQ_BETA, LQ_RHOBAR, LQ_PHIBAR, LQ_ANORM, LQ_DDNORM, LQ_XXNORM, LQ_Z, LQ_CS2, LQ_SN2, LQ_BNORM, LQ_RES2,

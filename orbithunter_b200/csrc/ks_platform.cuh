@@ -14,4 +14,33 @@ using std::fma;
   extern __shared__ __align__(16) unsigned char ks_dyn_smem_[];  \
   type* name = reinterpret_cast<type*>(ks_dyn_smem_)
 #define KS_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// thread-block clusters (sm_90+): rank / size / barrier / distributed-shared-memory mapping, and the launch with a
+// cluster dimension.  tests/emul/cuda_emul.h provides the same names on CPU threads.
+#include <cooperative_groups.h>
+__device__ __forceinline__ unsigned ks_cluster_rank() { return cooperative_groups::this_cluster().block_rank(); }
+__device__ __forceinline__ unsigned ks_cluster_size() { return cooperative_groups::this_cluster().num_blocks(); }
+__device__ __forceinline__ void ks_cluster_sync() { cooperative_groups::this_cluster().sync(); }
+template <class T>
+__device__ __forceinline__ T* ks_cluster_map(T* p, unsigned rank) {
+  return cooperative_groups::this_cluster().map_shared_rank(p, rank);
+}
+template <class... KArgs, class... Args>
+inline cudaError_t ks_launch_cluster(void (*kernel)(KArgs...), unsigned grid, unsigned block, unsigned cluster, size_t smem,
+                                     cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define KS_LAUNCH_CLUSTER(kernel, grid, block, cluster, smem, stream, ...) \
+  ks_launch_cluster(kernel, grid, block, cluster, smem, stream, __VA_ARGS__)
 #endif

@@ -123,8 +123,20 @@ struct Sums {
 };
 
 // P = true-scaled tuple of the forward transform of (u*u); W receives the spectrum of the second inverse transform.
+// tuples a stage needs from global memory besides P (loaded by the caller, so that it can batch the loads)
 template <int CLS, int OP>
-KS_DEVI void stage1_point(const OrbitCtx& c, const Geom& g, int j, int kp, const Tup& P, Tup& W, Sums& s) {
+KS_DEVI void stage1_loads(const OrbitCtx& c, const Geom& g, int j, int kp, Tup& Mt, Tup& V) {
+  Mt = gload<CLS>(c.Mo, j, kp, g);
+  if constexpr (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) V = gload<CLS>(c.Vo, j, kp, g);
+}
+template <int CLS, int OP>
+KS_DEVI Tup stage2_load(const OrbitCtx& c, const Geom& g, int j, int kp) {
+  return (OP == KS_OP_MATVEC || OP == KS_OP_COSTGRAD) ? gload<CLS>(c.Fo, j, kp, g) : gload<CLS>(c.Vo, j, kp, g);
+}
+
+template <int CLS, int OP>
+KS_DEVI void stage1_point(const OrbitCtx& c, const Geom& g, int j, int kp, const Tup& P, const Tup& Mt, const Tup& V, Tup& W,
+                          Sums& s) {
   constexpr bool REL = (CLS == KS_RELATIVE);
   const double w = (j == 0) ? 0.0 : c.wbase * (j * (1.0 / g.n));
   const double q = c.qbase * ((kp + 1) * (1.0 / g.m));
@@ -133,7 +145,6 @@ KS_DEVI void stage1_point(const OrbitCtx& c, const Geom& g, int j, int kp, const
   const double sig = c.sig;
   Tup N{-qn * P.b1, -qn * P.b2, qn * P.a1, qn * P.a2};
   gproject<CLS>(N, j);
-  const Tup Mt = gload<CLS>(c.Mo, j, kp, g);
   if constexpr (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) {
     Tup F;
     F.a1 = fma(d, Mt.a1, fma(-w, Mt.a2, N.a1));
@@ -159,14 +170,12 @@ KS_DEVI void stage1_point(const OrbitCtx& c, const Geom& g, int j, int kp, const
       W = dx_tup(F, q);
     }
   } else if constexpr (OP == KS_OP_RMATVEC) {
-    const Tup V = gload<CLS>(c.Vo, j, kp, g);
     const double dd = REL ? q * rot_x(Mt, V) : 0.0;
     s.e += fma(e, dot_tup(Mt, V), fma(sig, dd, -dot_tup(N, V)));
     s.x += w * rot_t(Mt, V);
     s.d += dd;
     W = dx_tup(V, q);
   } else {
-    const Tup V = gload<CLS>(c.Vo, j, kp, g);
     const double vt = c.vt, vx = c.vx, vs = c.vs;
     const double cdx = REL ? (-sig * vt + sig * vx + vs) * q : 0.0, cdt = vt * w, ce = vx * e;
     Tup R;
@@ -219,18 +228,19 @@ KS_DEVI void finish_scalars(const KsEvalArgs& a, const Geom& g, const OrbitCtx& 
 }
 
 // P = true-scaled tuple of the forward transform of (second field * u).
+// V0 = stage2_load(): F (costgrad), J v's first part (matvec) or v (rmatvec)
 template <int CLS, int OP>
-KS_DEVI void stage2_point(const OrbitCtx& c, const Geom& g, int j, int kp, const Tup& P) {
+KS_DEVI void stage2_point(const OrbitCtx& c, const Geom& g, int j, int kp, const Tup& P, const Tup& V0) {
   constexpr bool REL = (CLS == KS_RELATIVE);
   const double w = (j == 0) ? 0.0 : c.wbase * (j * (1.0 / g.n));
   const double q = c.qbase * ((kp + 1) * (1.0 / g.m));
   const double q2 = q * q, q4 = q2 * q2, d = q4 - q2;
   Tup R;
   if constexpr (OP == KS_OP_MATVEC) {
-    const Tup A0 = gload<CLS>(c.Fo, j, kp, g);
+    const Tup& A0 = V0;
     R = Tup{fma(-q, P.b1, A0.a1), fma(-q, P.b2, A0.a2), fma(q, P.a1, A0.b1), fma(q, P.a2, A0.b2)};
   } else {
-    const Tup V = (OP == KS_OP_COSTGRAD) ? gload<CLS>(c.Fo, j, kp, g) : gload<CLS>(c.Vo, j, kp, g);
+    const Tup& V = V0;
     R.a1 = fma(d, V.a1, fma(w, V.a2, -P.a1));
     R.a2 = fma(d, V.a2, fma(-w, V.a1, -P.a2));
     R.b1 = fma(d, V.b1, fma(w, V.b2, -P.b1));

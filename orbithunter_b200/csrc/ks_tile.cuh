@@ -9,8 +9,8 @@
 //   C  colfwd<stage 1> XC -> tuples -> F, scalar partial sums, second spectrum -> XC (forward + inverse FFT per line)
 //   D  row<MODE_MUL>   XC -> second field * u -> XC
 //   E  colfwd<stage 2> XC -> tuples -> output
-// plus a one-thread-per-orbit finalize kernel that adds the per-tile partial sums in a fixed order (deterministic cost
-// and parameter components).  A length-N line FFT is done by T = 8 or 16 adjacent lanes: each lane holds N/T points in
+// The per-tile partial sums behind cost and parameter components are added in a fixed order (deterministic) by pass E
+// (a one-thread-per-orbit finalize kernel for eqn, which has no pass E).  A length-N line FFT is done by T = 8 or 16 adjacent lanes: each lane holds N/T points in
 // registers, does radix-8/16 sub-FFTs there (ks_fft_reg.cuh) and exchanges once through a padded shared-memory line;
 // between a row pass' inverse and forward transforms the data never leaves registers (the lane-to-point assignment of the
 // output distribution equals that of the input distribution).  Global accesses are 64-256 byte contiguous segments.
@@ -65,6 +65,7 @@ struct LineFft {
   using P = Plan<N>;
   static constexpr int N1 = P::N1, N2 = P::N2, T = P::T, C1 = N2 / T, C2 = N1 / T, PT = N / T;
   static constexpr int LS = ((N + N1 + 7) / 8) * 8 + 1;  // line stride (double2): >= N1 * (N2 + 1), = 1 mod 8
+  static constexpr int TW = C1 * N1 * T;                 // shared twiddle table entries (double2)
   // register layouts (element index minus the lane's g):
   //   "pre"  slot c * N1 + n1   <-> N2 * n1 + T * c      (input of a transform)
   //   "post" slot c2 * N2 + k2  <-> T * c2 + N1 * k2     (output of a transform)
@@ -75,18 +76,18 @@ struct LineFft {
       if (pre_index(s) == off) return s;
     return -1;
   }
-  double twr[C1 * N1], twi[C1 * N1];  // W_N^{n2 k1}, forward sign
+  const double2* tws;  // tws[(c * N1 + k1) * T + g] = W_N^{(g + T c) k1}, forward sign (conflict-free, shared by all lines)
   int g;
-  KS_DEVI void init(int g_) {
+  // whole CTA: fill the twiddle table (visible after the next __syncthreads)
+  KS_DEVI static void fill_table(double2* tab) {
+    for (int i = threadIdx.x; i < TW; i += blockDim.x) {
+      const int gg = i % T, ck = i / T, k1 = ck % N1, c = ck / N1;
+      tab[i] = g_tw[N + (gg + T * c) * k1];
+    }
+  }
+  KS_DEVI void init(int g_, const double2* tab) {
     g = g_;
-#pragma unroll
-    for (int c = 0; c < C1; ++c)
-#pragma unroll
-      for (int k1 = 0; k1 < N1; ++k1) {
-        const double2 w = g_tw[N + (g_ + T * c) * k1];
-        twr[c * N1 + k1] = w.x;
-        twi[c * N1 + k1] = w.y;
-      }
+    tws = tab + g_;
   }
   // pre layout in, post layout out; X[k] = sum_n x[n] exp(-i SIGN 2 pi k n / N), unnormalised.  `line` is this line's
   // shared-memory buffer (LS double2), used for the one exchange.  All lanes of the warp must call.
@@ -106,7 +107,8 @@ struct LineFft {
       e[0] = make_double2(xr[0], xi[0]);
 #pragma unroll
       for (int k1 = 1; k1 < N1; ++k1) {
-        const double wr = twr[c * N1 + k1], wi = SIGN > 0 ? twi[c * N1 + k1] : -twi[c * N1 + k1];
+        const double2 w = tws[(c * N1 + k1) * T];
+        const double wr = w.x, wi = SIGN > 0 ? w.y : -w.y;
         e[k1 * (N2 + 1)] = make_double2(fma(xr[k1], wr, -xi[k1] * wi), fma(xr[k1], wi, xi[k1] * wr));
       }
     });
@@ -163,7 +165,7 @@ struct TileArgs {
 KS_HD constexpr int col_lines(int N) { return kThreads / (N == 256 ? 16 : 8); }
 template <int N>
 KS_HD constexpr size_t tile_smem_bytes() {
-  return (size_t)(kThreads / LineFft<N>::T) * LineFft<N>::LS * 16 + kWarps * 4 * 8;
+  return ((size_t)(kThreads / LineFft<N>::T) * LineFft<N>::LS + LineFft<N>::TW) * 16 + kWarps * 4 * 8;
 }
 
 KS_DEVI void spec_store(double2* ln, int j, int N, const Tup& t) {
@@ -176,30 +178,252 @@ KS_DEVI void spec_store(double2* ln, int j, int N, const Tup& t) {
   }
 }
 
+// One CTA = one tile (a block of lines of one orbit); the hardware scheduler balances tiles over SMs and co-resident CTAs
+// sit in different phases (global loads / FFT / stores), which is what hides the memory latency.  Every phase first issues
+// all of its global loads into registers and only then touches shared memory.
+
 // ---- pass A: modes -> XC ----------------------------------------------------------------------------------------------
 template <int CLS, int N>
 __global__ void __launch_bounds__(kThreads) tile_colinv_kernel(const TileArgs ta) {
   using F = LineFft<N>;
-  constexpr int KB = kThreads / F::T;
+  constexpr int KB = kThreads / F::T, H1 = N / 2, NIT = H1 * KB / kThreads;
   KS_DYN_SMEM(double2, smem);
+  double2* tab = smem + KB * F::LS;
   const Geom g = ta.g;
   const int ll = threadIdx.x / F::T, gi = threadIdx.x % F::T;
+  const int orbit = blockIdx.x / ta.nkb, k0 = (blockIdx.x - orbit * ta.nkb) * KB;
+  const double* Mo = ta.e.modes + (size_t)orbit * g.nm;
+  double2* XC = ta.XC + (size_t)orbit * g.k * N;
+  F::fill_table(tab);
   F f;
-  f.init(gi);
+  f.init(gi, tab);
   double2* ln = smem + ll * F::LS;
-  const int ntiles = ta.e.batch * ta.nkb;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int orbit = tile / ta.nkb, k0 = (tile - orbit * ta.nkb) * KB;
-    const double* Mo = ta.e.modes + (size_t)orbit * g.nm;
-    double2* XC = ta.XC + (size_t)orbit * g.k * N;
-    for (int idx = threadIdx.x; idx < (g.h + 1) * KB; idx += kThreads) {
-      const int kl = idx % KB, j = idx / KB, kp = k0 + kl;
-      Tup t{0.0, 0.0, 0.0, 0.0};
-      if (kp < g.k) t = gload<CLS>(Mo, j, kp, g);
-      spec_store(smem + kl * F::LS, j, N, t);
+  {
+    Tup t[NIT];
+    const int kl = threadIdx.x % KB, j0 = threadIdx.x / KB, kp = k0 + kl;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      t[i] = Tup{0.0, 0.0, 0.0, 0.0};
+      if (kp < g.k) t[i] = gload<CLS>(Mo, j0 + i * (kThreads / KB), kp, g);
+    }
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) spec_store(smem + kl * F::LS, j0 + i * (kThreads / KB), N, t[i]);
+  }
+  __syncthreads();
+  double vr[F::PT], vi[F::PT];
+#pragma unroll
+  for (int s = 0; s < F::PT; ++s) {
+    const double2 v = ln[gi + F::pre_index(s)];
+    vr[s] = v.x;
+    vi[s] = v.y;
+  }
+  f.template transform<-1>(vr, vi, ln);
+  const int kp = k0 + ll;
+  if (kp < g.k) {
+    double2* o = XC + (size_t)kp * N + gi;
+#pragma unroll
+    for (int s = 0; s < F::PT; ++s) o[F::post_index(s)] = make_double2(vr[s] * g.ct, vi[s] * g.ct);
+  }
+}
+
+// ---- passes B / D: rows ------------------------------------------------------------------------------------------------
+enum { MODE_SQ = 0, MODE_MUL = 1 };
+template <int M, int MODE>
+__global__ void __launch_bounds__(kThreads) tile_row_kernel(const TileArgs ta) {
+  using F = LineFft<M>;
+  constexpr int TB = kThreads / F::T, K = M / 2 - 1, NIT = (K * TB + kThreads - 1) / kThreads;
+  KS_DYN_SMEM(double2, smem);
+  double2* tab = smem + TB * F::LS;
+  const Geom g = ta.g;
+  const int n = g.n, n2 = n / 2;
+  const int ll = threadIdx.x / F::T, gi = threadIdx.x % F::T;
+  const int orbit = blockIdx.x / ta.ntb, t0 = (blockIdx.x - orbit * ta.ntb) * TB;
+  double2* XC = ta.XC + (size_t)orbit * K * n;
+  F::fill_table(tab);
+  F f;
+  f.init(gi, tab);
+  double2* ln = smem + ll * F::LS;
+  const int tl = threadIdx.x % TB, kq = threadIdx.x / TB;  // this thread's column of the tile, first wavenumber
+  {
+    double2 A[NIT], B[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int kp = kq + i * (kThreads / TB);
+      if (kp < K) {
+        A[i] = XC[(size_t)kp * n + t0 + tl];
+        B[i] = XC[(size_t)kp * n + t0 + tl + n2];
+      }
+    }
+    double2* l2 = smem + tl * F::LS;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int kp = kq + i * (kThreads / TB);
+      if (kp < K) {
+        l2[kp + 1] = make_double2(A[i].x - B[i].y, A[i].y + B[i].x);
+        l2[M - kp - 1] = make_double2(A[i].x + B[i].y, B[i].x - A[i].y);
+      }
+    }
+    if (threadIdx.x < TB) {
+      smem[threadIdx.x * F::LS] = make_double2(0.0, 0.0);
+      smem[threadIdx.x * F::LS + M / 2] = make_double2(0.0, 0.0);
+    }
+  }
+  double2* fu = ta.FU2 + ((size_t)orbit * n2 + t0 + ll) * M + gi;
+  double2 uf[MODE == MODE_MUL ? F::PT : 1];
+  if constexpr (MODE == MODE_MUL) {  // the stored field, issued before the inverse transform needs it
+#pragma unroll
+    for (int s = 0; s < F::PT; ++s) uf[s] = fu[F::post_index(s)];
+  }
+  __syncthreads();
+  double vr[F::PT], vi[F::PT];
+#pragma unroll
+  for (int s = 0; s < F::PT; ++s) {
+    const double2 v = ln[gi + F::pre_index(s)];
+    vr[s] = v.x;
+    vi[s] = v.y;
+  }
+  f.template transform<-1>(vr, vi, ln);
+#pragma unroll
+  for (int s = 0; s < F::PT; ++s) {
+    const double ua = vr[s] * g.cx, ub = vi[s] * g.cx;
+    if constexpr (MODE == MODE_SQ) {
+      fu[F::post_index(s)] = make_double2(ua, ub);
+      vr[s] = ua * ua;
+      vi[s] = ub * ub;
+    } else {
+      vr[s] = ua * uf[s].x;
+      vi[s] = ub * uf[s].y;
+    }
+  }
+  if (!ta.forward) return;
+  F::post_to_pre(vr, vi);
+  f.template transform<1>(vr, vi, ln);
+#pragma unroll
+  for (int s = 0; s < F::PT; ++s) ln[gi + F::post_index(s)] = make_double2(vr[s], vi[s]);
+  __syncthreads();
+  const double2* l2 = smem + tl * F::LS;
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    const int kp = kq + i * (kThreads / TB);
+    if (kp < K) {
+      const double2 y = l2[kp + 1], z = l2[M - kp - 1];
+      XC[(size_t)kp * n + t0 + tl] = make_double2((y.x + z.x) * g.cx, (y.y - z.y) * g.cx);
+      XC[(size_t)kp * n + t0 + tl + n2] = make_double2((y.y + z.y) * g.cx, (z.x - y.x) * g.cx);
+    }
+  }
+}
+
+KS_DEVI double warp_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// fixed-order sum of the per-tile partials of one orbit -> cost and parameter components
+template <int CLS, int OP>
+KS_DEVI void finalize_orbit(const TileArgs& ta, const kspw::OrbitCtx& c, int orbit) {
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int kb = 0; kb < ta.nkb; ++kb)
+    for (int i = 0; i < 4; ++i) t[i] += ta.partial[((size_t)orbit * ta.nkb + kb) * 4 + i];
+  kspw::finish_scalars<CLS, OP>(ta.e, ta.g, c, orbit, t[0], t[1], t[2], t[3]);
+}
+
+// ---- passes C / E: columns forward, tuple algebra, (C) second spectrum inverse ----------------------------------------
+template <int CLS, int OP, int N, int STAGE>
+__global__ void __launch_bounds__(kThreads) tile_colfwd_kernel(const TileArgs ta) {
+  using F = LineFft<N>;
+  constexpr int KB = kThreads / F::T, H1 = N / 2, NIT = H1 * KB / kThreads, JS = kThreads / KB;
+  constexpr bool REINV = (STAGE == 1 && OP != KS_OP_EQN);
+  KS_DYN_SMEM(double2, smem);
+  double2* tab = smem + KB * F::LS;
+  double* red = reinterpret_cast<double*>(tab + F::TW);  // [kWarps][4]
+  const Geom g = ta.g;
+  const KsEvalArgs& a = ta.e;
+  const int ll = threadIdx.x / F::T, gi = threadIdx.x % F::T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int orbit = blockIdx.x / ta.nkb, kb = blockIdx.x - orbit * ta.nkb, k0 = kb * KB;
+  double2* XC = ta.XC + (size_t)orbit * g.k * N;
+  const kspw::OrbitCtx c = kspw::make_ctx<CLS, OP>(a, g, orbit, ta.TU + (size_t)orbit * g.nm);
+  F::fill_table(tab);
+  F f;
+  f.init(gi, tab);
+  double2* ln = smem + ll * F::LS;
+  double vr[F::PT], vi[F::PT];
+  {
+    const int kp = k0 + ll;
+    const bool live = kp < g.k && !(STAGE == 1 && ta.zero_nuu);
+    const double2* src = XC + (size_t)(live ? kp : 0) * N + gi;
+#pragma unroll
+    for (int s = 0; s < F::PT; ++s) {
+      const double2 v = live ? src[F::pre_index(s)] : make_double2(0.0, 0.0);
+      vr[s] = v.x;
+      vi[s] = v.y;
+    }
+  }
+  // the tuples of u / v / F this tile's algebra needs: in flight during the forward transform
+  const int kl = threadIdx.x % KB, j0 = threadIdx.x / KB, kpw = k0 + kl;
+  const bool act = kpw < g.k;
+  Tup Mt[NIT], Vt[(STAGE == 1 && (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC)) ? NIT : 1];
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    if (!act) continue;
+    if constexpr (STAGE == 1) {
+      if constexpr (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) kspw::stage1_loads<CLS, OP>(c, g, j0 + i * JS, kpw, Mt[i], Vt[i]);
+      else kspw::stage1_loads<CLS, OP>(c, g, j0 + i * JS, kpw, Mt[i], Vt[0]);
+    } else {
+      Mt[i] = kspw::stage2_load<CLS, OP>(c, g, j0 + i * JS, kpw);
+    }
+  }
+  __syncthreads();  // twiddle table
+  f.template transform<1>(vr, vi, ln);
+#pragma unroll
+  for (int s = 0; s < F::PT; ++s) ln[gi + F::post_index(s)] = make_double2(vr[s], vi[s]);
+  __syncthreads();
+  kspw::Sums sm;
+  if (act) {
+    double2* l2 = smem + kl * F::LS;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int j = j0 + i * JS;
+      Tup P;
+      if (j == 0) {
+        const double c0 = ks::kSqrt2 * g.ct;
+        P = Tup{l2[0].x * c0, 0.0, l2[0].y * c0, 0.0};
+      } else {
+        const double2 y = l2[j], z = l2[N - j];
+        P = Tup{(y.x + z.x) * g.ct, (y.y - z.y) * g.ct, (y.y + z.y) * g.ct, (z.x - y.x) * g.ct};
+      }
+      if constexpr (STAGE == 1) {
+        Tup W{0.0, 0.0, 0.0, 0.0};
+        kspw::stage1_point<CLS, OP>(c, g, j, kpw, P, Mt[i], Vt[(OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) ? i : 0], W, sm);
+        if constexpr (REINV) spec_store(l2, j, N, W);
+      } else {
+        kspw::stage2_point<CLS, OP>(c, g, j, kpw, P, Mt[i]);
+      }
+    }
+  }
+  if constexpr (STAGE == 1) {
+    const double r0 = warp_sum(sm.ff), r1 = warp_sum(sm.e), r2 = warp_sum(fma(-c.sig, sm.d, sm.x)), r3 = warp_sum(sm.d);
+    if (lane == 0) {
+      red[warp * 4 + 0] = r0;
+      red[warp * 4 + 1] = r1;
+      red[warp * 4 + 2] = r2;
+      red[warp * 4 + 3] = r3;
     }
     __syncthreads();
-    double vr[F::PT], vi[F::PT];
+    if (threadIdx.x < 4) {
+      double t = 0.0;
+      for (int wq = 0; wq < kWarps; ++wq) t += red[wq * 4 + threadIdx.x];
+      ta.partial[((size_t)orbit * ta.nkb + kb) * 4 + threadIdx.x] = t;
+    }
+  } else {
+    // the per-tile partial sums of stage 1 are complete (previous launches): fold them here, once per orbit
+    if (OP != KS_OP_MATVEC && kb == 0 && threadIdx.x == 0) finalize_orbit<CLS, OP>(ta, c, orbit);
+  }
+  if constexpr (REINV) {
 #pragma unroll
     for (int s = 0; s < F::PT; ++s) {
       const double2 v = ln[gi + F::pre_index(s)];
@@ -213,192 +437,16 @@ __global__ void __launch_bounds__(kThreads) tile_colinv_kernel(const TileArgs ta
 #pragma unroll
       for (int s = 0; s < F::PT; ++s) o[F::post_index(s)] = make_double2(vr[s] * g.ct, vi[s] * g.ct);
     }
-    __syncthreads();
   }
 }
 
-// ---- passes B / D: rows ------------------------------------------------------------------------------------------------
-enum { MODE_SQ = 0, MODE_MUL = 1 };
-template <int M, int MODE>
-__global__ void __launch_bounds__(kThreads) tile_row_kernel(const TileArgs ta) {
-  using F = LineFft<M>;
-  constexpr int TB = kThreads / F::T;
-  KS_DYN_SMEM(double2, smem);
-  const Geom g = ta.g;
-  const int n = g.n, n2 = n / 2;
-  const int ll = threadIdx.x / F::T, gi = threadIdx.x % F::T;
-  F f;
-  f.init(gi);
-  double2* ln = smem + ll * F::LS;
-  const int ntiles = ta.e.batch * ta.ntb;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int orbit = tile / ta.ntb, t0 = (tile - orbit * ta.ntb) * TB;
-    double2* XC = ta.XC + (size_t)orbit * g.k * n;
-    for (int idx = threadIdx.x; idx < g.k * TB; idx += kThreads) {
-      const int tl = idx % TB, kp = idx / TB;
-      const double2 A = XC[(size_t)kp * n + t0 + tl], B = XC[(size_t)kp * n + t0 + tl + n2];
-      double2* l2 = smem + tl * F::LS;
-      l2[kp + 1] = make_double2(A.x - B.y, A.y + B.x);
-      l2[M - kp - 1] = make_double2(A.x + B.y, B.x - A.y);
-    }
-    if (threadIdx.x < TB) {
-      smem[threadIdx.x * F::LS] = make_double2(0.0, 0.0);
-      smem[threadIdx.x * F::LS + M / 2] = make_double2(0.0, 0.0);
-    }
-    __syncthreads();
-    double vr[F::PT], vi[F::PT];
-#pragma unroll
-    for (int s = 0; s < F::PT; ++s) {
-      const double2 v = ln[gi + F::pre_index(s)];
-      vr[s] = v.x;
-      vi[s] = v.y;
-    }
-    f.template transform<-1>(vr, vi, ln);
-    double2* fu = ta.FU2 + ((size_t)orbit * n2 + t0 + ll) * M + gi;
-#pragma unroll
-    for (int s = 0; s < F::PT; ++s) {
-      const double ua = vr[s] * g.cx, ub = vi[s] * g.cx;
-      if constexpr (MODE == MODE_SQ) {
-        fu[F::post_index(s)] = make_double2(ua, ub);
-        vr[s] = ua * ua;
-        vi[s] = ub * ub;
-      } else {
-        const double2 u = fu[F::post_index(s)];
-        vr[s] = ua * u.x;
-        vi[s] = ub * u.y;
-      }
-    }
-    if (ta.forward) {
-      F::post_to_pre(vr, vi);
-      f.template transform<1>(vr, vi, ln);
-#pragma unroll
-      for (int s = 0; s < F::PT; ++s) ln[gi + F::post_index(s)] = make_double2(vr[s], vi[s]);
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < g.k * TB; idx += kThreads) {
-        const int tl = idx % TB, kp = idx / TB;
-        const double2* l2 = smem + tl * F::LS;
-        const double2 y = l2[kp + 1], z = l2[M - kp - 1];
-        XC[(size_t)kp * n + t0 + tl] = make_double2((y.x + z.x) * g.cx, (y.y - z.y) * g.cx);
-        XC[(size_t)kp * n + t0 + tl + n2] = make_double2((y.y + z.y) * g.cx, (z.x - y.x) * g.cx);
-      }
-    }
-    __syncthreads();
-  }
-}
-
-KS_DEVI double warp_sum(double v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 16);
-  v += __shfl_xor_sync(0xffffffffu, v, 8);
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  return v;
-}
-
-// ---- passes C / E: columns forward, tuple algebra, (C) second spectrum inverse ----------------------------------------
-template <int CLS, int OP, int N, int STAGE>
-__global__ void __launch_bounds__(kThreads) tile_colfwd_kernel(const TileArgs ta) {
-  using F = LineFft<N>;
-  constexpr int KB = kThreads / F::T;
-  constexpr bool REINV = (STAGE == 1 && OP != KS_OP_EQN);
-  KS_DYN_SMEM(double2, smem);
-  double* red = reinterpret_cast<double*>(smem + KB * F::LS);  // [kWarps][4]
-  const Geom g = ta.g;
-  const KsEvalArgs& a = ta.e;
-  const int ll = threadIdx.x / F::T, gi = threadIdx.x % F::T;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  F f;
-  f.init(gi);
-  double2* ln = smem + ll * F::LS;
-  const int ntiles = a.batch * ta.nkb;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int orbit = tile / ta.nkb, kb = tile - orbit * ta.nkb, k0 = kb * KB;
-    double2* XC = ta.XC + (size_t)orbit * g.k * N;
-    const kspw::OrbitCtx c = kspw::make_ctx<CLS, OP>(a, g, orbit, ta.TU + (size_t)orbit * g.nm);
-    double vr[F::PT], vi[F::PT];
-    {
-      const int kp = k0 + ll;
-      const bool live = kp < g.k && !(STAGE == 1 && ta.zero_nuu);
-      const double2* src = XC + (size_t)(live ? kp : 0) * N + gi;
-#pragma unroll
-      for (int s = 0; s < F::PT; ++s) {
-        const double2 v = live ? src[F::pre_index(s)] : make_double2(0.0, 0.0);
-        vr[s] = v.x;
-        vi[s] = v.y;
-      }
-    }
-    f.template transform<1>(vr, vi, ln);
-#pragma unroll
-    for (int s = 0; s < F::PT; ++s) ln[gi + F::post_index(s)] = make_double2(vr[s], vi[s]);
-    __syncthreads();
-    kspw::Sums sm;
-    for (int idx = threadIdx.x; idx < (g.h + 1) * KB; idx += kThreads) {
-      const int kl = idx % KB, j = idx / KB, kp = k0 + kl;
-      if (kp >= g.k) continue;
-      double2* l2 = smem + kl * F::LS;
-      Tup P;
-      if (j == 0) {
-        const double c0 = ks::kSqrt2 * g.ct;
-        P = Tup{l2[0].x * c0, 0.0, l2[0].y * c0, 0.0};
-      } else {
-        const double2 y = l2[j], z = l2[N - j];
-        P = Tup{(y.x + z.x) * g.ct, (y.y - z.y) * g.ct, (y.y + z.y) * g.ct, (z.x - y.x) * g.ct};
-      }
-      if constexpr (STAGE == 1) {
-        Tup W{0.0, 0.0, 0.0, 0.0};
-        kspw::stage1_point<CLS, OP>(c, g, j, kp, P, W, sm);
-        if constexpr (REINV) spec_store(l2, j, N, W);
-      } else {
-        kspw::stage2_point<CLS, OP>(c, g, j, kp, P);
-      }
-    }
-    if constexpr (STAGE == 1) {
-      const double r0 = warp_sum(sm.ff), r1 = warp_sum(sm.e), r2 = warp_sum(fma(-c.sig, sm.d, sm.x)), r3 = warp_sum(sm.d);
-      if (lane == 0) {
-        red[warp * 4 + 0] = r0;
-        red[warp * 4 + 1] = r1;
-        red[warp * 4 + 2] = r2;
-        red[warp * 4 + 3] = r3;
-      }
-    }
-    __syncthreads();
-    if constexpr (STAGE == 1) {
-      if (threadIdx.x < 4) {
-        double t = 0.0;
-        for (int wq = 0; wq < kWarps; ++wq) t += red[wq * 4 + threadIdx.x];
-        ta.partial[((size_t)orbit * ta.nkb + kb) * 4 + threadIdx.x] = t;
-      }
-    }
-    if constexpr (REINV) {
-#pragma unroll
-      for (int s = 0; s < F::PT; ++s) {
-        const double2 v = ln[gi + F::pre_index(s)];
-        vr[s] = v.x;
-        vi[s] = v.y;
-      }
-      f.template transform<-1>(vr, vi, ln);
-      const int kp = k0 + ll;
-      if (kp < g.k) {
-        double2* o = XC + (size_t)kp * N + gi;
-#pragma unroll
-        for (int s = 0; s < F::PT; ++s) o[F::post_index(s)] = make_double2(vr[s] * g.ct, vi[s] * g.ct);
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// one thread per orbit: fixed-order sum of the per-tile partials -> cost and parameter components
+// eqn only (no stage 2): one thread per orbit
 template <int CLS, int OP>
 __global__ void tile_finalize_kernel(const TileArgs ta) {
   const int orbit = blockIdx.x * blockDim.x + threadIdx.x;
   if (orbit >= ta.e.batch) return;
-  const Geom g = ta.g;
-  const kspw::OrbitCtx c = kspw::make_ctx<CLS, OP>(ta.e, g, orbit, ta.TU + (size_t)orbit * g.nm);
-  double t[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int kb = 0; kb < ta.nkb; ++kb)
-    for (int i = 0; i < 4; ++i) t[i] += ta.partial[((size_t)orbit * ta.nkb + kb) * 4 + i];
-  kspw::finish_scalars<CLS, OP>(ta.e, g, c, orbit, t[0], t[1], t[2], t[3]);
+  const kspw::OrbitCtx c = kspw::make_ctx<CLS, OP>(ta.e, ta.g, orbit, ta.TU + (size_t)orbit * ta.g.nm);
+  finalize_orbit<CLS, OP>(ta, c, orbit);
 }
 
 // workspace doubles per orbit of a chunk

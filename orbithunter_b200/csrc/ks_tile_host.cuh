@@ -26,10 +26,7 @@ int tile_ctas_per_sm(K kern, size_t smem) {
 }
 template <class K>
 int tile_launch(K kern, size_t smem, int ntiles, const kst::TileArgs& ta, cudaStream_t s) {
-  static int per_sm = 0;  // one static per kernel instantiation
-  if (!per_sm) per_sm = tile_ctas_per_sm(kern, smem);
-  const int cap = sm_count() * per_sm;
-  KS_LAUNCH(kern, ntiles < cap ? ntiles : cap, kst::kThreads, smem, s, ta);
+  KS_LAUNCH(kern, ntiles, kst::kThreads, smem, s, ta);  // one CTA per tile
   return 0;
 }
 int tile_ensure_twiddles(cudaStream_t s) {
@@ -73,7 +70,7 @@ int tile_chunk_run(kst::TileArgs& ta, cudaStream_t s) {
   ta.zero_nuu = nuu ? 0 : 1;
   tile_row<kst::MODE_SQ>(ta, s);
   tile_colfwd<CLS, OP, N, 1>(ta, s);
-  if constexpr (OP != KS_OP_MATVEC) {
+  if constexpr (OP == KS_OP_EQN) {
     KS_LAUNCH((kst::tile_finalize_kernel<CLS, OP>), (ta.e.batch + 127) / 128, 128, 0, s, ta);
   }
   if constexpr (OP != KS_OP_EQN) {

@@ -69,6 +69,10 @@ struct BlockCtx {
 struct ThreadCtx {
   dim3 tid, bid, bdim, gdim;
   BlockCtx* blk;
+  // thread-block cluster (launch_cluster): the blocks of one cluster run concurrently
+  unsigned cluster_rank = 0, cluster_size = 1;
+  BlockCtx* const* cluster_blocks = nullptr;
+  std::barrier<>* cluster_bar = nullptr;
 };
 inline thread_local ThreadCtx tctx;
 inline int device_sm_count = 4;  // tiny "GPU" so persistent loops iterate
@@ -160,4 +164,63 @@ void launch(Kernel kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... arg
 }
 }  // namespace ks_emul
 
+namespace ks_emul {
+// grid.x must be a multiple of `cluster`; the `cluster` blocks of one cluster run concurrently (one OS thread per CUDA
+// thread), clusters one after another.  Kernels launched this way must keep ALL shared memory in the dynamic buffer
+// (KS_DYN_SMEM): `__shared__` statics are a single instance per process here.
+template <class Kernel, class... Args>
+void launch_cluster(Kernel kernel, unsigned grid, unsigned block, unsigned cluster, size_t smem_bytes, Args... args) {
+  const unsigned nwarps = (block + 31) / 32;
+  for (unsigned c0 = 0; c0 < grid; c0 += cluster) {
+    std::vector<BlockCtx> blks(cluster);
+    std::vector<BlockCtx*> ptrs(cluster);
+    std::vector<std::vector<unsigned char>> mem(cluster);
+    for (unsigned r = 0; r < cluster; ++r) {
+      BlockCtx& blk = blks[r];
+      blk.nthreads = block;
+      blk.block_bar = std::make_unique<std::barrier<>>(block);
+      for (unsigned w = 0; w < nwarps; ++w) blk.warp_bar.emplace_back(std::make_unique<std::barrier<>>(std::min(32u, block - 32 * w)));
+      blk.shfl.assign(nwarps * 32, 0);
+      mem[r].resize(smem_bytes + 64);
+      blk.smem = mem[r].data() + ((64 - (reinterpret_cast<uintptr_t>(mem[r].data()) & 63)) & 63);
+      ptrs[r] = &blk;
+    }
+    std::barrier<> cbar(cluster * block);
+    std::vector<std::thread> ts;
+    ts.reserve(cluster * block);
+    for (unsigned r = 0; r < cluster; ++r)
+      for (unsigned t = 0; t < block; ++t)
+        ts.emplace_back([&, r, t]() {
+          tctx.tid = dim3(t);
+          tctx.bid = dim3(c0 + r);
+          tctx.bdim = dim3(block);
+          tctx.gdim = dim3(grid);
+          tctx.blk = ptrs[r];
+          tctx.cluster_rank = r;
+          tctx.cluster_size = cluster;
+          tctx.cluster_blocks = ptrs.data();
+          tctx.cluster_bar = &cbar;
+          kernel(args...);
+          cbar.arrive_and_drop();  // a block that returned no longer takes part in cluster barriers
+        });
+    for (auto& th : ts) th.join();
+  }
+}
+}  // namespace ks_emul
+static inline unsigned ks_cluster_rank() { return ks_emul::tctx.cluster_rank; }
+static inline unsigned ks_cluster_size() { return ks_emul::tctx.cluster_size; }
+static inline void ks_cluster_sync() {
+  if (ks_emul::tctx.cluster_bar) ks_emul::tctx.cluster_bar->arrive_and_wait();
+}
+template <class T>
+static inline T* ks_cluster_map(T* p, unsigned rank) {
+  auto& c = ks_emul::tctx;
+  if (!c.cluster_blocks) return p;
+  const size_t off = reinterpret_cast<unsigned char*>(p) - c.blk->smem;
+  return reinterpret_cast<T*>(c.cluster_blocks[rank]->smem + off);
+}
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+
 #define KS_LAUNCH(kernel, grid, block, smem, stream, ...) ks_emul::launch(kernel, dim3(grid), dim3(block), smem, __VA_ARGS__)
+#define KS_LAUNCH_CLUSTER(kernel, grid, block, cluster, smem, stream, ...) \
+  (ks_emul::launch_cluster(kernel, grid, block, cluster, smem, __VA_ARGS__), cudaSuccess)

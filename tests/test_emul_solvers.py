@@ -50,8 +50,9 @@ def test_adjoint_descent_exit_codes():
     assert relerr(Mo[0], rm) < 1e-12
 
 
-@pytest.mark.parametrize("cid,method,precond", [(1, 0, False), (2, 0, True), (0, 1, False)])
-def test_newton_krylov_matches_scipy_based_oracle(cid, method, precond):
+@pytest.mark.parametrize("cid,method,precond,gm_cluster", [(1, 0, False, 1), (2, 0, True, 4), (0, 0, True, 0), (0, 0, False, 2),
+                                                          (0, 1, False, 1)])
+def test_newton_krylov_matches_scipy_based_oracle(cid, method, precond, gm_cluster):
     """Device GMRES (normal equations, optional diagonal M) / LSQR vs the oracle, which calls SciPy's own solvers as
     the reference does: same outer status / nit; GMRES trajectories agree to round-off, LSQR to its own sensitivity."""
     n = m = 16
@@ -64,7 +65,11 @@ def test_newton_krylov_matches_scipy_based_oracle(cid, method, precond):
         kw, okw = dict(restart=10, inner=2, rtol=1e-5), dict(restart=10, maxiter=2)
     else:
         kw, okw = dict(inner=30, atol=1e-6), dict(iter_lim=30)
-    Mo, po, status, nit, cost, cnt = E.newton_krylov(cid, n, m, M, p, cmask, method, maxiter=2, precond=precond, **kw)
+    E.lib().ks_debug_gmres_cluster(gm_cluster)  # GMRES step: 0 one CTA per orbit, 1 auto, 2/4 CTAs per orbit (cluster)
+    try:
+        Mo, po, status, nit, cost, cnt = E.newton_krylov(cid, n, m, M, p, cmask, method, maxiter=2, precond=precond, **kw)
+    finally:
+        E.lib().ks_debug_gmres_cluster(1)
     for b in range(B):
         rm, rp, st = ko.newton_krylov(M[b], p[b], cid, method="gmres" if method == 0 else "lsqr", maxiter=2,
                                       preconditioning=precond, scipy_kwargs=okw)

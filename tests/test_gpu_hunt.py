@@ -122,6 +122,32 @@ def test_gmres_converges_status_1(gold_hunt):
     assert np.allclose(r.orbit.parameters, g["hunt/rpo_gmres/out_params"], rtol=1e-8)
 
 
+@pytest.mark.parametrize("shape,B,mode", [((32, 32), 9, 4), ((64, 64), 5, 2), ((128, 128), 3, 1), ((256, 256), 2, 1)])
+def test_gmres_cluster_step_matches_single_cta_step(shape, B, mode):
+    """Two implementations of the GMRES step (thread-block cluster with register-resident slices vs one CTA per orbit):
+    same outer status / nit, cost and state to round-off (only the association of the dot-product sums differs)."""
+    from orbithunter_b200 import BatchedOrbitKS, _lib
+    from orbithunter_b200.optimize import hunt
+    from oracle import ks_oracle as ko
+
+    n, m = shape
+    T, L = (200.0, 200.0) if n == 256 else (60.0, 44.0)
+    M = np.stack([ko.populate_state(T, L, n, m, s, 0) for s in range(B)])
+    u = BatchedOrbitKS(M, np.tile([T, L, 0.0], (B, 1)), "OrbitKS")
+    kw = dict(maxiter=2, tol=1e-10, scipy_kwargs={"restart": 12, "maxiter": 2, "rtol": 1e-6})
+    L_ = _lib.lib()
+    try:
+        L_.ks_debug_gmres_cluster(mode)
+        a = hunt(u, "gmres", **kw)
+        L_.ks_debug_gmres_cluster(0)
+        b = hunt(u, "gmres", **kw)
+    finally:
+        L_.ks_debug_gmres_cluster(1)
+    assert torch.equal(a.status, b.status) and torch.equal(a.nit, b.nit)
+    assert torch.allclose(a.costs[-1], b.costs[-1], rtol=1e-9)
+    assert relerr(a.orbit.cpu_state(), b.orbit.cpu_state()) < 1e-9
+
+
 def test_hybrid_adj_then_gmres_batched_64():
     """BASELINE config 3 shape in miniature: 64x64 symmetry classes, adjoint warm-up then Newton-GMRES, vs the oracle."""
     from orbithunter_b200 import BatchedOrbitKS

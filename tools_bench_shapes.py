@@ -32,31 +32,32 @@ def timeit(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-from orbithunter_b200 import _lib  # noqa: E402
+if __name__ == "__main__":
+    from orbithunter_b200 import _lib  # noqa: E402
 
-chunks = [int(a) for a in sys.argv[1:]] or [64]
-out = []
-for chunk_mb in chunks:
-  _lib.lib().ks_debug_tile(1, chunk_mb)
-  for cls, n, m, T, L, B in (("OrbitKS", 32, 32, 44.0, 33.4, 4096), ("RelativeOrbitKS", 64, 64, 60.0, 44.0, 4096),
-                           ("ShiftReflectionOrbitKS", 64, 64, 60.0, 44.0, 4096), ("AntisymmetricOrbitKS", 64, 64, 60.0, 44.0, 4096),
-                           ("OrbitKS", 128, 128, 100.0, 100.0, 1024), ("OrbitKS", 256, 256, 200.0, 200.0, 64),
-                           ("OrbitKS", 256, 256, 200.0, 200.0, 512)):
-      if chunk_mb != chunks[0] and n == 32:
-          continue
-      M = seeds(cls, n, m, T, L, B)
-      p = np.tile([T, L, 0.0], (B, 1))
-      u = BatchedOrbitKS(M, p, cls)
-      v = BatchedOrbitKS(np.random.RandomState(0).randn(*M.shape), np.random.RandomState(1).randn(B, 3), cls)
-      nm = M.shape[1] * M.shape[2]
-      rec = {"class": cls, "grid": [n, m], "batch": B, "chunk_mb": chunk_mb}
-      ms = timeit(lambda: u.costgrad(), 20)
-      rec["costgrad_evals_per_s"] = B / ms * 1e3
-      rec["costgrad_alg_GBps"] = B * 8 * (2 * nm + 7) / ms / 1e6
-      ms = timeit(lambda: u.matvec(v), 20)
-      rec["matvec_per_s"] = B / ms * 1e3
-      ms = timeit(lambda: u.rmatvec(v), 20)
-      rec["rmatvec_per_s"] = B / ms * 1e3
-      rec["matvec_alg_GBps"] = B * 8 * (3 * nm + 9) / ms / 1e6
-      out.append(rec)
-      print(json.dumps(rec), flush=True)
+    chunks = [int(a) for a in sys.argv[1:]] or [64]
+    out = []
+    for chunk_mb in chunks:
+      _lib.lib().ks_debug_tile(1, chunk_mb)
+      for cls, n, m, T, L, B in (("OrbitKS", 32, 32, 44.0, 33.4, 4096), ("RelativeOrbitKS", 64, 64, 60.0, 44.0, 4096),
+                               ("ShiftReflectionOrbitKS", 64, 64, 60.0, 44.0, 4096), ("AntisymmetricOrbitKS", 64, 64, 60.0, 44.0, 4096),
+                               ("OrbitKS", 128, 128, 100.0, 100.0, 1024), ("OrbitKS", 256, 256, 200.0, 200.0, 64),
+                               ("OrbitKS", 256, 256, 200.0, 200.0, 512)):
+          if chunk_mb != chunks[0] and n == 32:
+              continue
+          M = seeds(cls, n, m, T, L, B)
+          p = np.tile([T, L, 0.0], (B, 1))
+          u = BatchedOrbitKS(M, p, cls)
+          v = BatchedOrbitKS(np.random.RandomState(0).randn(*M.shape), np.random.RandomState(1).randn(B, 3), cls)
+          nm = M.shape[1] * M.shape[2]
+          rec = {"class": cls, "grid": [n, m], "batch": B, "chunk_mb": chunk_mb}
+          ms = timeit(lambda: u.costgrad(), 20)
+          rec["costgrad_evals_per_s"] = B / ms * 1e3
+          rec["costgrad_alg_GBps"] = B * 8 * (2 * nm + 7) / ms / 1e6
+          ms = timeit(lambda: u.matvec(v), 20)
+          rec["matvec_per_s"] = B / ms * 1e3
+          ms = timeit(lambda: u.rmatvec(v), 20)
+          rec["rmatvec_per_s"] = B / ms * 1e3
+          rec["matvec_alg_GBps"] = B * 8 * (3 * nm + 9) / ms / 1e6
+          out.append(rec)
+          print(json.dumps(rec), flush=True)
