@@ -135,6 +135,56 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def hybrid_hunt(orb):
+    """BASELINE configs[0]/[1] end to end on the device: adjoint descent, then Newton-LSQR to cost 1e-10 (side measurement)."""
+    import torch
+
+    from orbithunter_b200.optimize import hunt
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = hunt(orb, ("adj", "lsqr"), maxiter=[10000, 60], tol=[1e-6, 1e-10], scipy_kwargs=[{}, {"iter_lim": 300}])
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    st = res.status.cpu().numpy()
+    return {"methods": "adj (maxiter 10000, tol 1e-6) -> lsqr (maxiter 60, iter_lim 300, tol 1e-10)", "orbits": int(st.size),
+            "wall_s": wall, "status_counts": {str(k): int((st == k).sum()) for k in (-1, 0, 1, 2, 3)},
+            "converged_orbits_per_s": float((st == 1).sum()) / wall, "median_final_cost": float(res.costs[-1].median().item())}
+
+
+def side_shapes(peak_gbs):
+    """Fused residual+adjoint evals/s at the other BASELINE shapes (configs 3 and 4) through the large-grid tile path;
+    side measurements, CUDA-event timed, inputs resident."""
+    import torch
+
+    from orbithunter_b200 import BatchedOrbitKS
+    from orbithunter_b200.ks import CLASSES
+
+    out = []
+    for cls, n, m, T, L, B in (("RelativeOrbitKS", 64, 64, 60.0, 44.0, 4096), ("ShiftReflectionOrbitKS", 64, 64, 60.0, 44.0, 4096),
+                               ("AntisymmetricOrbitKS", 64, 64, 60.0, 44.0, 4096), ("OrbitKS", 256, 256, 200.0, 200.0, 64)):
+        base = np.stack([CLASSES[cls](parameters=(T, L, 0.0)).populate(attr="state", seed=s, discretization=(n, m)).state
+                         for s in range(8)])
+        M = np.tile(base, ((B + 7) // 8, 1, 1))[:B] * (1.0 + 1e-3 * np.arange(B)[:, None, None] / B)
+        u = BatchedOrbitKS(M, np.tile([T, L, 0.0], (B, 1)), cls)
+        for _ in range(3):
+            u.costgrad()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 20
+        e0.record()
+        for _ in range(iters):
+            u.costgrad()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        nm = M.shape[1] * M.shape[2]
+        gbs = B * 8 * (2 * nm + 7) / ms / 1e6
+        out.append({"class": cls, "grid": [n, m], "batch": B, "evals_per_s": B / ms * 1e3, "algorithmic_GBps": gbs,
+                    "hbm_frac": gbs / peak_gbs, "kernels": "ks_tile.cuh: 5 line-block passes per evaluation"})
+    return out
+
+
 def make_seeds_cpu(count):
     from oracle import ks_oracle as ko
 
@@ -150,6 +200,7 @@ def main():
     ap.add_argument("--sets", type=int, default=4, help="distinct input/output sets rotated to exceed L2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hunt", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the side measurements (other BASELINE shapes, hybrid hunt)")
     ap.add_argument("--hunt-maxiter", type=int, default=10000)
     ap.add_argument("--variant", type=int, default=None, help="tuning: warp32 kernel variant (ks_debug_warp32_variant)")
     args = ap.parse_args()
@@ -262,8 +313,11 @@ def main():
                 "status_counts": {str(k): int((st == k).sum()) for k in (-1, 0, 1, 2, 3)},
                 "converged_orbits_per_s": float((st == 1).sum()) / wall,
                 "median_final_cost": float(res.costs[-1].median().item()),
-                "note": "one GPU (rank 0), one fused costgrad launch + one decision kernel per outer pass",
+                "note": "this rank's 4096 seeds; one fused launch per outer pass (decide on the previous trial, form and "
+                        "evaluate the next one)",
             }
+            if rank == 0 and not args.no_side:
+                hunt_stats["hybrid"] = hybrid_hunt(orb)
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -301,15 +355,18 @@ def main():
                    "l2": f"rotating {len(sets)} input/output sets ({len(sets) * BATCH * ALG_BYTES_PER_EVAL / 1e6:.0f} MB) > 126 MB L2",
                    "parallelism": f"orbits sharded over {world} GPU(s), no data-path collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "ks_warp32_kernel<OrbitKS,COSTGRAD>",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "ks_warp32x1_kernel<OrbitKS,COSTGRAD>",
                      "algorithmic_bytes_per_launch": BATCH * ALG_BYTES_PER_EVAL,
-                     "note": "fp64-pipe bound by design (SURVEY 7/8d): ~3.7k fp64 instr per warp-eval of 2 orbits"},
+                     "note": "binding resource is the fp64 pipe, not HBM: ~83k fp64 lane-instructions per eval, so 100 % of the "
+                             "fp64 pipe (64 lanes/clk/SM) is ~224 M evals/s = 0.52 of this HBM roofline (DESIGN.md section 4)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * (NM + 3) * 8,
                 "d2h_bytes_per_step": BATCH * (NM + 3 + 1) * 8, "steps": e2e_steps},
         "gpu_launches": args.steps, "clocks": clocks.summary(), "checksum_cost_sum": checksum,
     }
     if hunt_stats is not None:
         line["adjoint_descent"] = hunt_stats
+    if not args.no_side:
+        line["other_shapes"] = side_shapes(peak)
     if not args.no_cpu_baseline:
         cores = 1
         sample = 256
