@@ -52,6 +52,12 @@ int ks_mode_size(int cls, int n, int m);
 /* scratch bytes required by any of the calls below for this shape and batch. */
 size_t ks_workspace_bytes(int cls, int n, int m, int batch);
 
+/* OrbitKS._populate_state (ks/orbits.py:1738-1849, default 'laplace' x 'gaussian' modulation) for a batch of integer
+ * seeds: the reference's np.random.seed(seed); randn(n-1, cols) stream (legacy MT19937 + polar Box-Muller) reproduced on
+ * the device, one warp per seed.  seeds [B] uint32, params [B,3] (T, L, S), modes_out [B, Nm]. */
+int ks_populate_state(int cls, int n, int m, int batch, const uint32_t* seeds, const double* params, double* modes_out,
+                      void* stream);
+
 /* OrbitKS.transform (ks/orbits.py:231-303) and the class-specific overrides: any basis -> any basis. */
 int ks_transform(int cls, int n, int m, int batch, int from_basis, int to_basis, const double* in, double* out,
                  void* ws, size_t ws_bytes, void* stream);

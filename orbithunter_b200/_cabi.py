@@ -11,6 +11,7 @@ _SIG = {
     "ks_debug_gmres_cluster": (None, [C.c_int]),
     "ks_mode_size": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "ks_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ks_populate_state": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "ks_transform": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "ks_eqn": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "ks_matvec": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_uint32, _P, _P, C.c_size_t, _P]),

@@ -92,6 +92,37 @@ class BatchedOrbitKS:
             cons.update(constraints)
         self.constraints = cons
 
+    @classmethod
+    def from_seeds(cls, seeds, parameters, cls_name="OrbitKS", discretization=(32, 32), constraints=None, device=None):
+        """Random initial conditions generated ON THE DEVICE: the batch equivalent of the reference's
+        ``Cls(parameters=(T, L, S)).populate(attr="state", seed=s, discretization=(n, m))`` (ks/orbits.py:1738-1849,
+        default modulations) for every integer seed ``s`` in ``seeds`` (NumPy's legacy MT19937 / randn stream).
+        ``parameters`` is (3,) or (B, 3).  RelativeOrbitKS: S is reset to 0 as the reference's populate does (:2872-2883)."""
+        if not torch.cuda.is_available():
+            raise _lib.KsB200Error("orbithunter_b200 needs a CUDA device; there is no CPU path")
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        cid = CLASS_IDS[cls_name] if isinstance(cls_name, str) else int(cls_name)
+        seeds_np = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64).ravel())
+        if seeds_np.size and (seeds_np.min() < 0 or seeds_np.max() > 2**32 - 1):
+            raise ValueError("Seed must be between 0 and 2**32 - 1")
+        B = int(seeds_np.size)
+        n, m = (int(x) for x in discretization)
+        par = torch.as_tensor(np.ascontiguousarray(parameters, dtype=np.float64)).reshape(-1, 3)
+        if par.shape[0] == 1 and B != 1:
+            par = par.expand(B, 3)
+        par = par.contiguous().to(dev)
+        if par.shape[0] != B:
+            raise ValueError("parameters must have shape (3,) or (len(seeds), 3)")
+        if cid == 1:
+            par[:, 2] = 0.0
+        sd = torch.as_tensor(seeds_np.astype(np.uint32).view(np.int32)).to(dev)
+        state = torch.empty((B,) + basis_shape(cid, n, m, "modes"), dtype=torch.float64, device=dev)
+        if B:
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().ks_populate_state(cid, n, m, B, sd.data_ptr(), par.data_ptr(), state.data_ptr(),
+                                                        torch.cuda.current_stream().cuda_stream))
+        return cls(state, par, cid, "modes", (n, m), constraints)
+
     # ---- bookkeeping -------------------------------------------------------------------------------------------
     @property
     def n(self):

@@ -1,0 +1,110 @@
+"""Numerical continuation in one parameter (reference orbithunter/continuation.py:10-136), on the device hunt().
+
+``continuation`` is the single-orbit drop-in: same arguments, same loop (constrain, step the constrained parameter
+towards its target, re-converge with ``hunt``, stop at the first non-converged step).  ``continuation_batch`` runs the
+same loop for a whole BatchedOrbitKS in lock step, one family member per orbit slot, each with its own current value and
+target: an orbit stops moving as soon as one of its hunts does not converge (its last converged member is kept), the
+loop ends when every orbit has either reached its target or failed.  ``save=True`` (HDF5 output, io.py) is outside the
+hot path and raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .batch import PARAMETER_LABELS, BatchedOrbitKS
+from .optimize import OrbitResult, hunt
+
+__all__ = ["continuation", "continuation_batch"]
+
+
+def _equals_target(value, target):
+    """continuation.py:10-18: equality up to 13 decimals."""
+    return np.round(value, 13) == np.round(target, 13)
+
+
+def _next_extent(current, target, increment):
+    """continuation.py:45-50: step, but never past the target."""
+    if np.sign(target - (current + increment)) != np.sign(increment):
+        return target
+    return current + increment
+
+
+def _parse_item(constraint_item):
+    if isinstance(constraint_item, type({}.items())):
+        return tuple(*constraint_item)
+    if isinstance(constraint_item, dict):
+        return tuple(*constraint_item.items())
+    if isinstance(constraint_item, tuple):
+        return constraint_item
+    raise TypeError("constraint_item is expected to be dict, dict_item, tuple containing a single key, value pair.")
+
+
+def _constrained(cls_defaults, labels):
+    """Orbit.constrain (core.py:2069-2115): the given labels are held fixed, every other parameter gets its default."""
+    return {key: True if key in labels else cls_defaults.get(key, True) for key in PARAMETER_LABELS}
+
+
+def continuation(orbit_instance, constraint_item, *extra_constraints, step_size=0.01, **kwargs):
+    """Drop-in for orbithunter.continuation.continuation on an OrbitKS-family instance (continuation.py:59-136)."""
+    if kwargs.get("save", False):
+        raise NotImplementedError("save=True writes HDF5 through io.py, which is outside the B200 hot path")
+    label, target = _parse_item(constraint_item)
+    orbit_instance.constraints = _constrained(orbit_instance._default_constraints(), (label, *extra_constraints))
+    result = OrbitResult(orbit=orbit_instance, status=1)
+    step = np.sign(target - getattr(result.orbit, label)) * np.abs(step_size)
+    while result.status == 1 and not _equals_target(getattr(result.orbit, label), target):
+        o = result.orbit
+        nxt = _next_extent(getattr(o, label), target, step)
+        params = tuple(nxt if lab == label else getattr(o, lab) for lab in o.parameter_labels())
+        result = hunt(o._new(parameters=params), **kwargs)
+    return result
+
+
+def continuation_batch(batch: BatchedOrbitKS, label, targets, *extra_constraints, step_size=0.01, max_steps=100000, **kwargs):
+    """Lock-step continuation of every orbit of ``batch`` in parameter ``label`` towards ``targets`` (scalar or (B,)).
+
+    Returns OrbitResult(orbit=BatchedOrbitKS of the last converged member of each family, status=(B,) int32 with 1 where
+    the target was reached and otherwise the status of the failing hunt, steps=(B,) accepted continuation steps,
+    reached=(B,) bool).  The starting orbits are assumed converged (the reference assumes the same, continuation.py:101).
+    """
+    if kwargs.get("save", False):
+        raise NotImplementedError("save=True writes HDF5 through io.py, which is outside the B200 hot path")
+    if label not in PARAMETER_LABELS:
+        raise ValueError(f"unknown parameter label {label!r}")
+    col = PARAMETER_LABELS.index(label)
+    cur = batch.transform("modes").copy()
+    from .batch import default_constraints
+
+    cur.constraints = _constrained(default_constraints(cur.cls_id), (label, *extra_constraints))
+    B, dev = cur.batch, cur.state.device
+    target = torch.as_tensor(np.broadcast_to(np.asarray(targets, dtype=np.float64), (B,)).copy(), device=dev)
+    value = cur.parameters[:, col]
+    sign = torch.sign(target - value)
+    step = sign * abs(float(step_size))
+    status = torch.ones(B, dtype=torch.int32, device=dev)
+    steps = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    def at_target(v):
+        return torch.round(v, decimals=13) == torch.round(target, decimals=13)
+
+    for _ in range(int(max_steps)):
+        value = cur.parameters[:, col]
+        moving = (status == 1) & ~at_target(value)
+        if not bool(moving.any()):
+            break
+        stepped = value + step
+        overshoot = torch.sign(target - stepped) != sign
+        nxt = torch.where(overshoot, target, stepped)
+        trial = cur.copy()
+        trial.parameters[:, col] = torch.where(moving, nxt, value)
+        res = hunt(trial, **{k: (v.copy() if hasattr(v, "copy") else v) for k, v in kwargs.items()})
+        ok = moving & (res.status == 1)
+        failed = moving & (res.status != 1)
+        keep = ok[:, None, None]
+        cur.state = torch.where(keep, res.orbit.state, cur.state)
+        cur.parameters = torch.where(ok[:, None], res.orbit.parameters, cur.parameters)
+        status = torch.where(failed, res.status.to(torch.int32), status)
+        steps = steps + ok.to(torch.int32)
+    reached = at_target(cur.parameters[:, col])
+    return OrbitResult(orbit=cur, status=status, steps=steps, reached=reached)

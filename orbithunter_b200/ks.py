@@ -400,9 +400,11 @@ class OrbitKS:
         n, m = kwargs.get("discretization", None) or self.discretization or self._default_shape()
         self.discretization = (int(n), int(m))
         rows, cols = self.shapes()[2]
-        kx = np.arange(1, m // 2)
+        # the reference truncates its floating-point frequency tables (spatial_frequencies(2 pi, m, 1), :1788-1791) with
+        # .astype(int); for m, n that are not powers of two a few entries land on kappa - 1 -- same expression here
+        kx = np.abs((2 * np.pi * m / (2 * np.pi)) * (np.arange(0, m // 2 + 1) * (1.0 / m))[1:-1]).astype(int)
         space_ = np.concatenate((kx, kx))[None, :cols]
-        jt = np.arange(1, n // 2)
+        jt = np.abs((-1 * (2 * np.pi * n / (2 * np.pi))) * (np.arange(0, n // 2 + 1) * (1.0 / n))[1:-1]).astype(int)
         time_ = np.concatenate(([0], jt, jt))[:, None]
         random_modes = np.random.randn(rows, cols)
         norm0 = np.linalg.norm(random_modes)

@@ -47,6 +47,15 @@ def basis_shape(cls, n, m, basis):
     return {0: (n, m), 1: (n, m - 2), 2: mode_shape(cls, n, m)}[basis]
 
 
+def populate(cls, n, m, seeds, params):
+    L = lib()
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    params = np.ascontiguousarray(params, dtype=float)
+    out = np.zeros((len(seeds),) + mode_shape(cls, n, m))
+    _chk(L, L.ks_populate_state(cls, n, m, len(seeds), _p(seeds), _p(params), _p(out), None))
+    return out
+
+
 def transform(cls, n, m, arr, frm, to):
     L = lib()
     arr = np.ascontiguousarray(arr, dtype=float)

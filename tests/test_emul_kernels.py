@@ -138,3 +138,15 @@ def test_derivatives_and_precondition(cid):
     out, gp = E.precondition(cid, n, m, V, vp, p, cmask)
     eo, egp = ko.precondition(V, vp, p, n, m, cid, cons)
     assert relerr(out, eo) < 1e-13 and np.allclose(gp, egp, rtol=1e-13)
+
+
+@pytest.mark.parametrize("cid,shape", [(0, (32, 32)), (1, (16, 24)), (2, (64, 64)), (3, (26, 34))])
+def test_device_seed_generator_matches_reference_stream(cid, shape):
+    """ks_populate_state: NumPy's legacy seed -> MT19937 -> randn stream and the reference's modulation, per seed."""
+    n, m = shape
+    seeds = np.array([0, 1, 7, 12345, 2**32 - 1], dtype=np.uint64)
+    params = np.stack([[44.0 + 3 * i, 33.4 + 5 * i, 0.0] for i in range(len(seeds))])
+    out = E.populate(cid, n, m, seeds, params)
+    for i, s in enumerate(seeds):
+        ref = ko.populate_state(params[i, 0], params[i, 1], n, m, int(s), cid)
+        assert relerr(out[i], ref) < 1e-14

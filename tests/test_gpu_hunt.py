@@ -184,3 +184,64 @@ def test_newton_descent_matrix_free():
     assert r.nit == 1
     if c1 <= c0:  # full step accepted by the reference logic
         assert relerr(r.orbit.state, expect.state) < 1e-7 and abs(r.costs[-1] - c1) < 1e-7 * max(1.0, c1)
+
+
+def test_continuation_matches_reference_family():
+    """continuation() (reference continuation.py:59-136) on the device hunt, against the family members the
+    unmodified reference reaches from its stored rpo (tests/golden/ks_continuation.npz, oracle/make_golden_continuation.py):
+    single-orbit drop-in and the lock-step batch form."""
+    import os
+
+    from orbithunter_b200 import BatchedOrbitKS, RelativeOrbitKS
+    from orbithunter_b200.continuation import continuation, continuation_batch
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ks_continuation.npz"))
+    kw = dict(methods="gmres", maxiter=40, tol=1e-6, scipy_kwargs={"restart": 50, "maxiter": 4, "rtol": 1e-8})
+    for tag in ("up", "down"):
+        o = RelativeOrbitKS(state=g["start/modes"], basis="modes", parameters=tuple(g["start/params"]))
+        r = continuation(o, ("t", float(g[tag + "/target"])), step_size=float(g[tag + "/step"]),
+                         **{k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()})
+        assert r.status == int(g[tag + "/status"]) == 1
+        assert np.allclose(r.orbit.parameters, g[tag + "/params"], rtol=1e-7)
+        assert relerr(r.orbit.state, g[tag + "/modes"]) < 1e-6
+        assert r.orbit.cost() < 1e-6
+    B = 3
+    T0 = float(g["start/params"][0])
+    batch = BatchedOrbitKS(np.repeat(g["start/modes"][None], B, 0), np.repeat(g["start/params"][None], B, 0), "RelativeOrbitKS")
+    targets = np.array([float(g["up/target"]), float(g["down/target"]), T0])
+    rb = continuation_batch(batch, "t", targets, step_size=0.02, **kw)
+    assert rb.status.tolist() == [1, 1, 1] and rb.reached.tolist() == [True, True, True] and rb.steps.tolist() == [3, 2, 0]
+    P = rb.orbit.cpu_parameters()
+    assert np.allclose(P[0], g["up/params"], rtol=1e-7) and np.allclose(P[1], g["down/params"], rtol=1e-7)
+    assert np.array_equal(P[2], g["start/params"])
+    S = rb.orbit.cpu_state()
+    assert relerr(S[0], g["up/modes"]) < 1e-6 and relerr(S[1], g["down/modes"]) < 1e-6 and np.array_equal(S[2], g["start/modes"])
+
+
+def test_device_seed_generator(gold_eval):
+    """BatchedOrbitKS.from_seeds (ks_populate_state, MT19937 + legacy randn on the device) against the
+    reference generator's outputs in tests/golden and the oracle, incl. sizes where the reference's integer truncation of
+    its frequency tables matters, and a large batch against the host generator."""
+    from orbithunter_b200 import BatchedOrbitKS, OrbitKS
+    from orbithunter_b200.batch import CLASS_NAMES
+
+    g = gold_eval
+    for key in sorted({k.rsplit("/", 1)[0] for k in g.files if k.startswith("random/") and k.endswith("/seed")}):
+        cid = int(key.split("/")[1].split("_")[0])
+        M, p = g[key + "/modes"], g[key + "/params"]
+        n, m = ko.field_shape(M, cid)
+        b = BatchedOrbitKS.from_seeds([int(g[key + "/seed"])], (float(p[0]), float(p[1]), 0.0), CLASS_NAMES[cid], (n, m))
+        assert relerr(b.cpu_state()[0], M) < 1e-13, key
+    for cid in range(4):
+        for (n, m) in ((16, 24), (26, 34), (64, 64), (256, 256)):
+            seeds = [0, 5, 2**32 - 1]
+            b = BatchedOrbitKS.from_seeds(seeds, (60.0, 44.0, 0.0), CLASS_NAMES[cid], (n, m))
+            for i, s in enumerate(seeds):
+                assert relerr(b.cpu_state()[i], ko.populate_state(60.0, 44.0, n, m, s, cid)) < 1e-13
+    B = 1000
+    b = BatchedOrbitKS.from_seeds(np.arange(B), (44.0, 33.4, 0.0), "OrbitKS", (32, 32))
+    host = np.stack([OrbitKS(parameters=(44.0, 33.4, 0.0)).populate(attr="state", seed=s, discretization=(32, 32)).state
+                     for s in range(B)])
+    assert relerr(b.cpu_state(), host) < 1e-13
+    with pytest.raises(ValueError):
+        BatchedOrbitKS.from_seeds([-1], (44.0, 33.4, 0.0))

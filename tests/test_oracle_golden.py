@@ -182,3 +182,28 @@ def test_hunt_outcomes(gold_hunt):
         Mo, po, st = ko.adjoint_descent(M, np.array([44.0, 33.4, 0.0]), ko.ORBIT, maxiter=1500)
         assert (ko.hunt_status(st, st["cost"], 1e-6), st["nit"]) == (int(row[1]), int(row[2]))
         assert abs(st["cost"] - row[3]) < 1e-9 and np.allclose(po[:2], row[4:6], rtol=1e-11)
+
+
+def test_product_host_populate_matches_reference_generator(gold_eval):
+    """The product's own host-side populate() (orbithunter_b200/ks.py, no GPU involved) against the reference's generator
+    outputs in tests/golden and against the oracle at sizes where the reference's integer truncation of its frequency
+    tables matters (m = 24, 34: ks/orbits.py:1788-1791)."""
+    from orbithunter_b200.ks import CLASSES
+    from orbithunter_b200.batch import CLASS_NAMES
+
+    g = gold_eval
+    n_checked = 0
+    for key in sorted({k.rsplit("/", 1)[0] for k in g.files if k.startswith("random/")}):
+        cid = int(key.split("/")[1].split("_")[0])
+        if key + "/seed" not in g.files:
+            continue
+        M, p = g[key + "/modes"], g[key + "/params"]
+        n, m = ko.field_shape(M, cid)
+        o = CLASSES[CLASS_NAMES[cid]](parameters=(float(p[0]), float(p[1]), 0.0)).populate(attr="state", seed=int(g[key + "/seed"]),
+                                                                                           discretization=(n, m))
+        assert relerr(o.state, M) < 1e-14, key
+        n_checked += 1
+    for cid in range(4):
+        for (n, m) in ((16, 24), (26, 34), (34, 26), (64, 64)):
+            o = CLASSES[CLASS_NAMES[cid]](parameters=(44.0, 33.4, 0.0)).populate(attr="state", seed=11, discretization=(n, m))
+            assert relerr(o.state, ko.populate_state(44.0, 33.4, n, m, 11, cid)) < 1e-14
