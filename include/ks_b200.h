@@ -42,6 +42,9 @@ void ks_debug_warp32_variant(int variant);
 /* tuning hook, large-grid (n, m in {64, 128, 256}) tile path: enabled = 0 routes those shapes through the generic
  * kernel (cross-check); chunk_mb > 0 sets the workspace budget that bounds how many orbits one pass sequence covers. */
 void ks_debug_tile(int enabled, int chunk_mb);
+/* tuning / test hook, 32x32 adjoint descent: passes every orbit runs inside one launch of the multi-pass kernel with its
+ * state on chip (default 128); 0 = the one-pass-per-launch kernel with the state in global memory (cross-check). */
+void ks_debug_adjoint_inner(int passes);
 /* test hook, GMRES step kernel: 1 (default) = thread-block cluster per orbit (1/2/4/8 CTAs by vector length), vector
  * slices in registers; 2/4/8 = at least that many CTAs per orbit; 0 = one CTA per orbit, vectors in HBM (cross-check;
  * also used automatically when N > 65536). */

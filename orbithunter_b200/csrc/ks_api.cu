@@ -54,7 +54,7 @@ int launch_warp32_as(const KsEvalArgs& a, cudaStream_t s) {
 template <int CLS, int OP, bool PC>
 int launch_warp32x1_pc(const KsEvalArgs& a, cudaStream_t s) {
   auto kern = ksx1::ks_warp32x1_kernel<CLS, OP, PC>;
-  constexpr int smem = ksx1::smem_bytes(OP == KS_OP_ADJSTEP);
+  constexpr int smem = ksx1::smem_bytes(OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI);
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -69,6 +69,10 @@ int launch_warp32x1_pc(const KsEvalArgs& a, cudaStream_t s) {
 template <int CLS>
 int launch_adjstep(const KsEvalArgs& a, cudaStream_t s) {
   return a.precond ? launch_warp32x1_pc<CLS, KS_OP_ADJSTEP, true>(a, s) : launch_warp32x1_pc<CLS, KS_OP_ADJSTEP, false>(a, s);
+}
+template <int CLS>
+int launch_adjmulti(const KsEvalArgs& a, cudaStream_t s) {
+  return a.precond ? launch_warp32x1_pc<CLS, KS_OP_ADJMULTI, true>(a, s) : launch_warp32x1_pc<CLS, KS_OP_ADJMULTI, false>(a, s);
 }
 template <int CLS, int OP>
 int launch_warp32(const KsEvalArgs& a, cudaStream_t s) {
@@ -96,6 +100,7 @@ int launch_generic(const ksg::GenArgs& ga, cudaStream_t s) {
 
 // ---- tile path (n, m in {64, 128, 256}): kernels and launch code live in ks_tile_c{0..3}.cu (one class per translation
 // unit, compiled in parallel); see ks_tile_host.cuh ----
+int g_adj_inner = 128;  // 32x32 adjoint descent: passes per launch of the multi-pass kernel (0 = one pass per launch)
 int g_gmres_cluster = 1;  // 0 = one CTA per orbit GMRES step (cross-check), 1 = auto cluster size, 2/4/8 = at least that size
 bool g_tile_enabled = true;
 int g_tile_chunk_mb = 256;
@@ -165,6 +170,7 @@ int ks_b200_abi_version(void) { return 1; }
 const char* ks_last_error(void) { return g_err; }
 
 void ks_debug_force_generic(int on) { g_force_generic = on != 0; }
+void ks_debug_adjoint_inner(int passes) { g_adj_inner = passes < 0 ? 0 : passes; }
 void ks_debug_gmres_cluster(int mode) { g_gmres_cluster = (mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8) ? mode : 1; }
 void ks_debug_tile(int enabled, int chunk_mb) {
   g_tile_enabled = enabled != 0;
@@ -453,6 +459,31 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
     cudaMemsetAsync(A.gp[0], 0, (size_t)batch * 24, s);
     const long max_passes = (long)maxiter + 1200;
     int passes = 0;
+    if (g_adj_inner > 0) {
+      // multi-pass kernel: every live orbit runs up to `inner` passes per launch with its state on chip; an orbit either
+      // counts an iteration or halves its step in each pass, so ceil(max_passes / inner) launches always suffice
+      A.inner = g_adj_inner;
+      for (long done = 0; done < max_passes + A.inner; done += A.inner) {
+        cudaMemsetAsync(A.n_live, 0, 4, s);
+        A.first = (done == 0) ? 1 : 0;
+        int rc;
+        switch (cls) {
+          case KS_ORBIT: rc = launch_adjmulti<KS_ORBIT>(a, s); break;
+          case KS_RELATIVE: rc = launch_adjmulti<KS_RELATIVE>(a, s); break;
+          case KS_SHIFT_REFLECTION: rc = launch_adjmulti<KS_SHIFT_REFLECTION>(a, s); break;
+          default: rc = launch_adjmulti<KS_ANTISYMMETRIC>(a, s); break;
+        }
+        if (rc != 0) return rc;
+        passes += A.inner;
+        int n_live = 0;
+        if (cudaMemcpyAsync(&n_live, A.n_live, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+          return fail(KS_ERR_LAUNCH, "adjoint descent: device error while polling the live-orbit counter");
+        if (n_live == 0) break;
+      }
+      KS_LAUNCH(adj_gather_kernel, batch, 128, 0, s, A, modes, params, cls, batch, (int)nm);
+      if (passes_out) *passes_out = passes;
+      return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "fused adjoint descent launch failed");
+    }
     for (long it = 0; it < max_passes; ++it) {
       cudaMemsetAsync(A.n_live, 0, 4, s);
       A.first = (it == 0) ? 1 : 0;

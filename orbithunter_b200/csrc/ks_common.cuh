@@ -8,7 +8,7 @@
 // :3582, :3189).  Numbering is shared with include/ks_b200.h and oracle/ks_oracle.py.
 enum { KS_ORBIT = 0, KS_RELATIVE = 1, KS_SHIFT_REFLECTION = 2, KS_ANTISYMMETRIC = 3 };
 // fused evaluation ops
-enum { KS_OP_EQN = 0, KS_OP_COSTGRAD = 1, KS_OP_MATVEC = 2, KS_OP_RMATVEC = 3, KS_OP_ADJSTEP = 5 };
+enum { KS_OP_EQN = 0, KS_OP_COSTGRAD = 1, KS_OP_MATVEC = 2, KS_OP_RMATVEC = 3, KS_OP_ADJSTEP = 5, KS_OP_ADJMULTI = 6 };
 // constraint mask bits (set = parameter held constant; reference core.py:1617-1664 `constraints`)
 enum { KS_FIX_T = 1, KS_FIX_X = 2, KS_FIX_S = 4 };
 
@@ -31,6 +31,7 @@ struct KsAdjFused {
   double tol, ftol, min_step;
   int maxiter;
   int first;       // first pass: evaluate u itself (initial cost and gradient), nothing to decide
+  int inner;       // KS_OP_ADJMULTI: passes each orbit runs inside one launch (state stays in shared memory / registers)
 };
 
 struct KsEvalArgs {
@@ -51,7 +52,7 @@ struct KsEvalArgs {
   int v_ld, out_ld;
   int v_tail;             // matvec: read (dT, dL, dS) from vmodes[b*v_ld + Nm + slot] instead of vparams
   int out_tail;           // rmatvec/costgrad: write free parameter components to out_state[b*out_ld + Nm + slot]
-  KsAdjFused adj;         // KS_OP_ADJSTEP only
+  KsAdjFused adj;         // KS_OP_ADJSTEP / KS_OP_ADJMULTI only
 };
 
 namespace ks {

@@ -94,10 +94,16 @@ KS_DEVI double warp_sum(double v) {
 
 template <int CLS, int OP, bool PC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const KsEvalArgs a) {
-  static_assert(OP == KS_OP_EQN || OP == KS_OP_COSTGRAD || OP == KS_OP_ADJSTEP, "eqn, costgrad and the fused adjoint step");
+  static_assert(OP == KS_OP_EQN || OP == KS_OP_COSTGRAD || OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI,
+                "eqn, costgrad and the fused adjoint steps");
+  // ADJ : one adjoint-descent pass per launch (decide on the previous trial, evaluate the next), state in global memory.
+  // ADJM: every orbit runs up to adj.inner passes inside one launch; its accepted point u and gradient g stay in the
+  //       warp's shared-memory stage (lane-private packed slots), the scalars in registers; the decision on a trial is
+  //       taken right after its evaluation.  Same arithmetic, hence the same decisions, as ADJ.
   constexpr bool ADJ = (OP == KS_OP_ADJSTEP);
-  constexpr bool GRAD = (OP == KS_OP_COSTGRAD) || ADJ;
-  constexpr int kWarpSmemDoubles = warp_smem_doubles(ADJ);
+  constexpr bool ADJM = (OP == KS_OP_ADJMULTI);
+  constexpr bool GRAD = (OP == KS_OP_COSTGRAD) || ADJ || ADJM;
+  constexpr int kWarpSmemDoubles = warp_smem_doubles(ADJ || ADJM);
   constexpr bool FULL = (CLS == KS_ORBIT || CLS == KS_RELATIVE);
   constexpr bool REL = (CLS == KS_RELATIVE);
   constexpr int COLS = FULL ? 30 : 15, NM = 31 * COLS;
@@ -213,16 +219,58 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
     }
     ksw32::cp_async_commit();
   };
-  Pending next = decide(gw);
-  prefetch(gw, next);
+  Pending next{0, 0, 0.0, 1.0, 1.0, 0.0};
+  if constexpr (!ADJM) {
+    next = decide(gw);
+    prefetch(gw, next);
+  }
 #pragma unroll 1
   for (int orbit = gw; orbit < a.batch; orbit += nw) {
-    const Pending pd = next;
-    next = decide(orbit + nw);
-    if (!pd.live) {  // (fused adjoint descent) this orbit has left the loop: nothing was staged for it
-      ksw32::cp_async_wait<0>();
-      prefetch(orbit + nw, next);
-      continue;
+    Pending pd = next;
+    // ADJM: this orbit's descent state (identical in every lane)
+    [[maybe_unused]] int st_live = 1, st_status = -1, st_nit = 0, st_first = 0;
+    [[maybe_unused]] double st_cost = 0.0, st_step = 0.0, st_T = 1.0, st_L = 1.0, st_S = 0.0, st_g0 = 0.0, st_g1 = 0.0, st_g2 = 0.0;
+    [[maybe_unused]] double ct = 0.0, tg0 = 0.0, tg1 = 0.0, tg2 = 0.0;
+    if constexpr (ADJM) {
+      const KsAdjFused& A = a.adj;
+      st_first = A.first;
+      st_live = A.first ? 1 : A.live[orbit];
+      if (!st_live) continue;
+      st_step = A.step[orbit];
+      st_cost = A.cost[orbit];
+      st_status = A.status[orbit];
+      st_nit = A.nit[orbit];
+      st_T = A.p[0][orbit * 3 + 0];
+      st_L = A.p[0][orbit * 3 + 1];
+      st_S = A.p[0][orbit * 3 + 2];
+      st_g0 = A.gp[0][orbit * 3 + 0];
+      st_g1 = A.gp[0][orbit * 3 + 1];
+      st_g2 = A.gp[0][orbit * 3 + 2];
+      const double* Un = A.u[0] + (size_t)orbit * kPackedDoubles + lane * 2;
+      const double* Gn = A.g[0] + (size_t)orbit * kPackedDoubles + lane * 2;
+#pragma unroll
+      for (int pr = 0; pr < 16; ++pr) {
+        cp_async16(pstage + pr * 64, Un + pr * 64);
+        cp_async16(pstage + kPackedDoubles + pr * 64, Gn + pr * 64);
+      }
+      ksw32::cp_async_commit();
+      pd.live = 1;
+    } else {
+      next = decide(orbit + nw);
+      if (!pd.live) {  // (fused adjoint descent) this orbit has left the loop: nothing was staged for it
+        ksw32::cp_async_wait<0>();
+        prefetch(orbit + nw, next);
+        continue;
+      }
+    }
+#pragma unroll 1
+    for (int it = 0; it < (ADJM ? a.adj.inner : 1); ++it) {
+    if constexpr (ADJM) {
+      if (!st_live) break;
+      pd.step = st_first ? 0.0 : st_step;  // trial point u - step * grad; the first evaluation is at u itself
+      pd.T = fma(-pd.step, st_g0, st_T);
+      pd.L = fma(-pd.step, st_g1, st_L);
+      pd.S = fma(-pd.step, st_g2, st_S);
     }
     const double T = pd.T, Lx = pd.L, S = pd.S;
     const double wbase = -1.0 * (ks::kTwoPi * 32.0 / T);
@@ -234,7 +282,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
     // ---------------- phase A (COL): half tuples of u -> A[t] or B[t] -> tile component h ----------------
     double m1[16], m2[16];  // half tuples (x1, x2) of u; overwritten by F in stage 1
     ksw32::cp_async_wait<0>();
-    if constexpr (ADJ) {
+    if constexpr (ADJ || ADJM) {
       // trial point u - step * grad (core.py:1760-1796 increment); slot 2J-1 = x1(J), slot 2J = x2(J), slot 0 = x1(0)
       m2[0] = 0.0;
 #pragma unroll
@@ -267,7 +315,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
         }
       }
     }
-    prefetch(orbit + nw, next);
+    if constexpr (!ADJM) prefetch(orbit + nw, next);
     {
       double x[32];
       double hr[16], hi[16];
@@ -385,6 +433,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
             A.tcost[orbit] = 0.5 * ff;
           }
         }
+      } else if constexpr (ADJM) {
+        ct = 0.5 * ff;
       } else {
         if (lane == 0 && a.out_cost) a.out_cost[orbit] = 0.5 * ff;
       }
@@ -394,13 +444,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
         double px = warp_sum(fma(e + d, s_mf, s_x - s_ff) * lw);
         double pt = warp_sum(fma(-sig, s_d, s_x) * lw);
         double ps = REL ? warp_sum(s_d * lw) : 0.0;
-        if (lane == 0 && (ADJ || a.out_params || a.out_tail)) {
+        if (ADJM || (lane == 0 && (ADJ || a.out_params || a.out_tail))) {
           double gt = fix_t ? 0.0 : (-1.0 / T) * pt, gx = fix_x ? 0.0 : (1.0 / Lx) * px, gs = fix_s ? 0.0 : (-1.0 / T) * ps;
           if constexpr (PC) {
             if (!fix_t) gt *= 1.0 / T;
             if (!fix_x) gx *= 1.0 / ((Lx * Lx) * (Lx * Lx));
           }
-          if constexpr (ADJ) {
+          if constexpr (ADJM) {
+            tg0 = gt;
+            tg1 = gx;
+            tg2 = gs;
+          } else if constexpr (ADJ) {
             double* gpp = a.adj.gp[a.adj.first ? pd.cur : pd.cur ^ 1] + orbit * 3;
             gpp[0] = gt;
             gpp[1] = gx;
@@ -470,7 +524,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
       pr[0] = (0.5 * ks::kSqrt2) * p0;
       pi[0] = 0.0;
       const int out_ld = a.out_ld ? a.out_ld : NM;
-      double* Op = ADJ ? nullptr : a.out_state + (size_t)orbit * out_ld + coff;
+      double* Op = (ADJ || ADJM) ? nullptr : a.out_state + (size_t)orbit * out_ld + coff;
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
         const bool pres = (J & 1) ? presO : presE;
@@ -488,7 +542,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
           g1 *= pm;
           g2 *= pm;
         }
-        if constexpr (ADJ) {  // keep the gradient half tuples (absent halves as zeros) for the packed store below
+        if constexpr (ADJ || ADJM) {  // keep the gradient half tuples (absent halves as zeros) for the packed store below
           m1[J] = pres ? g1 : 0.0;
           m2[J] = pres ? g2 : 0.0;
         } else {
@@ -504,8 +558,88 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
         for (int pr = 0; pr < 16; ++pr)
           *reinterpret_cast<double2*>(Gp + pr * 64) = make_double2(pr == 0 ? m1[0] : m2[pr], pr < 15 ? m1[pr + 1] : 0.0);
       }
+      if constexpr (ADJM) {
+        // judge this trial now (optimize.py:478-480 backtracking, _process_correction :2174-2189, loop exit :506-507): the
+        // same rules as decide() above, on registers; an accepted step rewrites u and g in the warp's stage
+        const KsAdjFused& A = a.adj;
+        bool take_g = false;
+        if (st_first) {  // initial F, cost and gradient (optimize.py:462-467)
+          st_first = 0;
+          st_cost = ct;
+          st_live = ct > A.tol ? 1 : 0;
+          take_g = true;
+        } else if (ct >= st_cost && st_step > A.min_step) {
+          st_step *= 0.5;
+        } else {
+          int accept = 0;
+          st_nit += 1;
+          if (ct <= A.tol) {
+            st_status = -1;
+            accept = 1;
+          } else if (st_step <= A.min_step) {
+            st_status = 0;
+          } else if (st_nit == A.maxiter) {
+            st_status = 2;
+            accept = (ct < st_cost) ? 1 : 0;
+          } else {
+            const double big = fmax(fmax(st_cost, ct), 1.0);
+            if ((st_cost - ct) / big < A.ftol) st_status = 3; else accept = 1;
+          }
+          if (accept) {
+            st_cost = ct;
+#pragma unroll
+            for (int pr = 0; pr < 16; ++pr) {
+              double2 uu = *reinterpret_cast<const double2*>(pstage + pr * 64);
+              const double2 gg = *reinterpret_cast<const double2*>(pstage + kPackedDoubles + pr * 64);
+              uu.x = fma(-pd.step, gg.x, uu.x);
+              uu.y = fma(-pd.step, gg.y, uu.y);
+              *reinterpret_cast<double2*>(pstage + pr * 64) = uu;
+            }
+            st_T = T;
+            st_L = Lx;
+            st_S = S;
+            take_g = true;
+          }
+          st_live = (st_cost > A.tol && st_status == -1) ? 1 : 0;
+          if (!st_live && st_cost <= A.tol) st_status = -1;
+        }
+        if (take_g) {
+#pragma unroll
+          for (int pr = 0; pr < 16; ++pr)
+            *reinterpret_cast<double2*>(pstage + kPackedDoubles + pr * 64) =
+                make_double2(pr == 0 ? m1[0] : m2[pr], pr < 15 ? m1[pr + 1] : 0.0);
+          st_g0 = tg0;
+          st_g1 = tg1;
+          st_g2 = tg2;
+        }
+      }
     }
     __syncwarp();  // the tile is rewritten by the next orbit's phase A (other lanes' columns are read in phase E)
+    }  // passes of this orbit (one unless ADJM)
+    if constexpr (ADJM) {
+      const KsAdjFused& A = a.adj;
+      double* Uo = A.u[0] + (size_t)orbit * kPackedDoubles + lane * 2;
+      double* Go = A.g[0] + (size_t)orbit * kPackedDoubles + lane * 2;
+#pragma unroll
+      for (int pr = 0; pr < 16; ++pr) {
+        *reinterpret_cast<double2*>(Uo + pr * 64) = *reinterpret_cast<const double2*>(pstage + pr * 64);
+        *reinterpret_cast<double2*>(Go + pr * 64) = *reinterpret_cast<const double2*>(pstage + kPackedDoubles + pr * 64);
+      }
+      if (lane == 0) {
+        A.cost[orbit] = st_cost;
+        A.step[orbit] = st_step;
+        A.status[orbit] = st_status;
+        A.nit[orbit] = st_nit;
+        A.live[orbit] = st_live;
+        A.p[0][orbit * 3 + 0] = st_T;
+        A.p[0][orbit * 3 + 1] = st_L;
+        A.p[0][orbit * 3 + 2] = st_S;
+        A.gp[0][orbit * 3 + 0] = st_g0;
+        A.gp[0][orbit * 3 + 1] = st_g1;
+        A.gp[0][orbit * 3 + 2] = st_g2;
+        if (st_live) atomicAdd(A.n_live, 1);
+      }
+    }
   }
 }
 

@@ -12,8 +12,16 @@ from conftest import relerr  # noqa: E402
 from oracle import ks_oracle as ko  # noqa: E402
 
 
+@pytest.fixture(params=[128, 7, 0], ids=["multi128", "multi7", "perpass"])
+def adj_inner(request):
+    """32x32 adjoint descent kernels: multi-pass (state on chip, 128 or 7 passes per launch) and one pass per launch."""
+    E.lib().ks_debug_adjoint_inner(request.param)
+    yield request.param
+    E.lib().ks_debug_adjoint_inner(128)
+
+
 @pytest.mark.parametrize("cid", range(4))
-def test_adjoint_descent_matches_oracle(cid):
+def test_adjoint_descent_matches_oracle(cid, adj_inner):
     n = m = 32
     B = 3
     M = np.stack([ko.populate_state(44.0, 44.0, n, m, 3 + s, cid) for s in range(B)])
@@ -31,7 +39,7 @@ def test_adjoint_descent_matches_oracle(cid):
         assert passes >= int(nit.max())
 
 
-def test_adjoint_descent_exit_codes():
+def test_adjoint_descent_exit_codes(adj_inner):
     """min-step (0), maxiter (2), insufficient decrease (3), already-converged (-1 with nit 0) per orbit in one batch."""
     n = m = 32
     M = np.stack([ko.populate_state(44.0, 44.0, n, m, 3, 0), 1e-9 * ko.populate_state(44.0, 44.0, n, m, 4, 0)])
