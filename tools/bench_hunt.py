@@ -1,16 +1,18 @@
 """Side measurements of the Newton-Krylov hunts at BASELINE configs 3 and 4 (bounded): wall time, outcome counts.
-python tools_bench_hunt.py [cfg3|cfg4|all] [B3] [B4]"""
+python tools/bench_hunt.py [cfg3|cfg4|all] [B3] [B4]"""
 import json
+import os
 import sys
 import time
 
 import numpy as np
 import torch
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from orbithunter_b200 import BatchedOrbitKS  # noqa: E402
 from orbithunter_b200.optimize import hunt  # noqa: E402
-from tools_bench_shapes import seeds  # noqa: E402
+from bench_shapes import seeds  # noqa: E402
 
 
 def run(tag, fn):

@@ -1,13 +1,15 @@
 """Side measurement: seeds/s of the device seed generator (BatchedOrbitKS.from_seeds) vs the host generator (the product's
-NumPy populate = the reference's algorithm) on one core.  python tools_bench_populate.py"""
+NumPy populate = the reference's algorithm) on one core.  python tools/bench_populate.py"""
 import json
+import os
 import sys
 import time
 
 import numpy as np
 import torch
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from orbithunter_b200 import BatchedOrbitKS, OrbitKS  # noqa: E402
 
 for (n, m, B) in ((32, 32, 65536), (64, 64, 16384), (256, 256, 512)):

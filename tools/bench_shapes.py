@@ -1,13 +1,15 @@
 """Side measurements (not the bench.py contract): evals/s of the fused costgrad and of matvec/rmatvec at the other
-BASELINE shapes, through BatchedOrbitKS, CUDA-event timed.  python tools_bench_shapes.py"""
+BASELINE shapes, through BatchedOrbitKS, CUDA-event timed.  python tools/bench_shapes.py"""
 import json
+import os
 import sys
 import time
 
 import numpy as np
 import torch
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from orbithunter_b200 import BatchedOrbitKS  # noqa: E402
 from orbithunter_b200.ks import CLASSES  # noqa: E402
 

@@ -1,13 +1,15 @@
 """Experiment: how many random 32x32 OrbitKS seeds converge under adj -> Newton hybrids, and how fast.
-python tools_converge.py B"""
+python tools/converge.py B"""
 import json
+import os
 import sys
 import time
 
 import numpy as np
 import torch
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from orbithunter_b200 import BatchedOrbitKS, OrbitKS  # noqa: E402
 from orbithunter_b200.optimize import hunt  # noqa: E402
 

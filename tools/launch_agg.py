@@ -1,4 +1,4 @@
-"""Aggregate an ncu launch list (--metrics gpu__time_duration.sum --csv) by kernel.  python tools_launch_agg.py file.csv"""
+"""Aggregate an ncu launch list (--metrics gpu__time_duration.sum --csv) by kernel.  python tools/launch_agg.py file.csv"""
 import collections
 import csv
 import re

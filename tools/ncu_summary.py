@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep (ncu --set full) per launch: duration, DRAM bytes, fp64 pipe, occupancy, top stall reasons.
-python tools_ncu_summary.py report.ncu-rep"""
+python tools/ncu_summary.py report.ncu-rep"""
 import csv
 import subprocess
 import sys

@@ -1,11 +1,13 @@
-"""Profiling helper: a short batched adjoint-descent run (4096 OrbitKS 32x32 seeds).  python tools_profile_adj.py [maxiter]"""
+"""Profiling helper: a short batched adjoint-descent run (4096 OrbitKS 32x32 seeds).  python tools/profile_adj.py [maxiter]"""
+import os
 import sys
 import time
 
 import numpy as np
 import torch
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from orbithunter_b200 import BatchedOrbitKS, OrbitKS  # noqa: E402
 from orbithunter_b200.optimize import hunt  # noqa: E402
 

@@ -1,13 +1,15 @@
 """Profiling helper for the large-grid tile path: repeated fused costgrad on one shape.
-python tools_profile_tile.py CLASS N M BATCH [iters] [chunk_mb]"""
+python tools/profile_tile.py CLASS N M BATCH [iters] [chunk_mb]"""
+import os
 import sys
 
 import numpy as np
 import torch
 
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from orbithunter_b200 import BatchedOrbitKS, _lib  # noqa: E402
-from tools_bench_shapes import seeds, timeit  # noqa: E402
+from bench_shapes import seeds, timeit  # noqa: E402
 
 if __name__ == "__main__":
     cls, n, m, B = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
