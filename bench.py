@@ -313,8 +313,8 @@ def main():
                 "status_counts": {str(k): int((st == k).sum()) for k in (-1, 0, 1, 2, 3)},
                 "converged_orbits_per_s": float((st == 1).sum()) / wall,
                 "median_final_cost": float(res.costs[-1].median().item()),
-                "note": "this rank's 4096 seeds; one fused launch per outer pass (decide on the previous trial, form and "
-                        "evaluate the next one)",
+                "note": "this rank's 4096 seeds; multi-pass kernel: each orbit runs up to 128 passes per launch with its point "
+                        "and gradient in shared memory (wall time includes the initial cost evaluation and the host polls)",
             }
             if rank == 0 and not args.no_side:
                 hunt_stats["hybrid"] = hybrid_hunt(orb)
