@@ -21,7 +21,7 @@ from oracle.h5mini import H5Mini  # noqa: E402
 
 warnings.filterwarnings("ignore")
 oh = refshim.load()
-from orbithunter.continuation import continuation  # noqa: E402
+from orbithunter.continuation import continuation, discretization_continuation  # noqa: E402
 
 KW = dict(methods="gmres", maxiter=40, tol=1e-6, scipy_kwargs={"restart": 50, "maxiter": 4, "rtol": 1e-8})
 
@@ -45,6 +45,23 @@ def main():
         out[f"{tag}/params"] = np.array(r.orbit.parameters, dtype=float)
         out[f"{tag}/cost"] = r.orbit.cost()
         print(tag, r.status, r.orbit.parameters, r.orbit.cost())
+    # discretization continuation (continuation.py:170-279) of the same orbit: 32x32 -> 32x36 (two re-converged steps)
+    s = oh.RelativeOrbitKS(**vars(start))
+    r = discretization_continuation(s, (32, 36), **{k: (dict(v) if isinstance(v, dict) else v) for k, v in KW.items()})
+    out["disc/target"] = np.array([32, 36])
+    out["disc/status"] = r.status
+    out["disc/shape"] = np.array(r.orbit.discretization)
+    out["disc/modes"] = r.orbit.state
+    out["disc/params"] = np.array(r.orbit.parameters, dtype=float)
+    out["disc/cost"] = r.orbit.cost()
+    print("disc", r.status, r.orbit.discretization, r.orbit.parameters, r.orbit.cost())
+    # resize (core.py:1167-1226; _pad / _truncate ks/orbits.py:1428-1564 and the subclass overrides) in the modes basis
+    classes = {0: oh.OrbitKS, 1: oh.RelativeOrbitKS, 2: oh.ShiftReflectionOrbitKS, 3: oh.AntisymmetricOrbitKS}
+    for cid, C in classes.items():
+        o = C(parameters=(44.0, 44.0, 0.0)).populate(attr="state", seed=4, discretization=(16, 24))
+        out[f"resize/{cid}/modes"] = o.state
+        for shape in ((16, 24), (20, 24), (16, 30), (12, 20), (24, 16), (32, 32)):
+            out[f"resize/{cid}/{shape[0]}x{shape[1]}"] = o.resize(*shape).state
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ks_continuation.npz"), **out)
 
 

@@ -15,7 +15,7 @@ import torch
 from .batch import PARAMETER_LABELS, BatchedOrbitKS
 from .optimize import OrbitResult, hunt
 
-__all__ = ["continuation", "continuation_batch"]
+__all__ = ["continuation", "continuation_batch", "discretization_continuation"]
 
 
 def _equals_target(value, target):
@@ -108,3 +108,40 @@ def continuation_batch(batch: BatchedOrbitKS, label, targets, *extra_constraints
         steps = steps + ok.to(torch.int32)
     reached = at_target(cur.parameters[:, col])
     return OrbitResult(orbit=cur, status=status, steps=steps, reached=reached)
+
+
+def _increment_discretization(orbit_instance, target_size, increment, axis=0):
+    """continuation.py:139-167: one step of the discretization along ``axis``, never past the target."""
+    current = orbit_instance.shapes()[0][axis]
+    nxt = target_size if np.sign(target_size - (current + increment)) != np.sign(increment) else current + increment
+    shape = tuple(int(d) if i != axis else int(nxt) for i, d in enumerate(orbit_instance.shapes()[0]))
+    return orbit_instance.resize(*shape)
+
+
+def discretization_continuation(orbit_instance, target_discretization, cycle=False, **kwargs):
+    """Drop-in for orbithunter.continuation.discretization_continuation (continuation.py:170-279): change the grid of a
+    converged orbit step by step (zero padding / truncation of the modes), re-converging with ``hunt`` after every step."""
+    if kwargs.get("save", False):
+        raise NotImplementedError("save=True writes HDF5 through io.py, which is outside the B200 hot path")
+    target_discretization = tuple(int(x) for x in target_discretization)
+    result = OrbitResult(orbit=orbit_instance, status=1)
+    axes_order = np.array(kwargs.get("axes_order", np.argsort(target_discretization)[::-1]))
+    step_sizes = kwargs.get("step_sizes", np.array(orbit_instance.minimal_shape_increments())[axes_order])
+    hunt_kwargs = {k: v for k, v in kwargs.items() if k not in ("axes_order", "step_sizes")}
+
+    def fresh():
+        return {k: (v.copy() if hasattr(v, "copy") else v) for k, v in hunt_kwargs.items()}
+
+    if cycle:
+        idx = 0
+        while result.status == 1 and tuple(result.orbit.shapes()[0]) != target_discretization:
+            ax = axes_order[idx]
+            step = np.sign(target_discretization[ax] - result.orbit.shapes()[0][ax]) * np.abs(step_sizes[ax])
+            result = hunt(_increment_discretization(result.orbit, target_discretization[ax], step, axis=ax), **fresh())
+            idx = np.mod(idx + 1, len(axes_order))
+    else:
+        for ax in axes_order:
+            step = np.abs(step_sizes[ax]) * np.sign(target_discretization[ax] - result.orbit.shapes()[0][ax])
+            while result.status == 1 and not result.orbit.shapes()[0][ax] == target_discretization[ax]:
+                result = hunt(_increment_discretization(result.orbit, target_discretization[ax], step, axis=ax), **fresh())
+    return result

@@ -360,6 +360,69 @@ class OrbitKS:
         return self.__class__(**{**vars(self), **kwargs, "state": self.state + step_size * other.state, "parameters": params})
 
     # ---- seeds (ks/orbits.py:1738-1849, core.py:2016-2044, :2434-2514; default modulations only) ----------------------
+    # ---- rediscretization (reference core.py:1167-1226, ks/orbits.py:1428-1564): zero padding / truncation of the modes ----
+    def resize(self, *new_discretization, **kwargs):
+        new_shape = new_discretization
+        if len(new_shape) == 1 and isinstance(new_shape[0], tuple):
+            new_shape = tuple(new_shape[0])
+        if not new_shape:
+            raise NotImplementedError("resize() without an explicit shape (dimension_based_discretization) is not provided")
+        new_shape = tuple(int(x) for x in new_shape)
+        out = self.copy().transform(to="modes")
+        if tuple(self.discretization) != new_shape:
+            for ax, (old, new, min_size) in enumerate(zip(self.discretization, new_shape, self.minimal_shape())):
+                if new < min_size:
+                    raise ValueError("minimum discretization requirements not met during resize.")
+                if new < old:
+                    out = out._truncate(new, axis=ax)
+                elif new > old:
+                    out = out._pad(new, axis=ax)
+        return out.transform(to=self.basis)
+
+    @staticmethod
+    def _check_even(size):
+        if np.mod(size, 2):
+            raise ValueError("New discretization size must be an even number, preferably a power of 2")
+
+    def _pad(self, size, axis=0, **kwargs):
+        modes = self.transform(to="modes")
+        self._check_even(size)
+        n, m = modes.discretization
+        if axis == 0:
+            h, padding = n // 2 - 1, (size - n) // 2
+            padded = np.concatenate((modes.state[:-h, :], np.pad(modes.state[-h:, :], ((padding, padding), (0, 0)))), axis=0)
+            padded = padded * np.sqrt(size / n)
+            disc = (size, m)
+        else:
+            padded = self._pad_space(modes.state, m, size) * np.sqrt(size / m)
+            disc = (n, size)
+        return self._new(state=padded, basis="modes", discretization=disc).transform(to=self.basis)
+
+    def _truncate(self, size, axis=0):
+        modes = self.transform(to="modes")
+        self._check_even(size)
+        n, m = modes.discretization
+        keep = int(size // 2) - 1
+        if axis == 0:
+            h = n // 2 - 1
+            first, second = modes.state[: keep + 1, :], modes.state[-h:, :][:keep, :]
+            truncated = np.sqrt(size / n) * np.concatenate((first, second), axis=0)
+            disc = (size, m)
+        else:
+            truncated = np.sqrt(size / m) * self._truncate_space(modes.state, m, keep)
+            disc = (n, size)
+        return self._new(state=truncated, basis="modes", discretization=disc).transform(to=self.basis)
+
+    @staticmethod
+    def _pad_space(state, m, size):  # columns [Re_x | Im_x]: zeros after each block (ks/orbits.py:1470-1480)
+        k, padding = m // 2 - 1, (size - m) // 2
+        return np.concatenate((state[:, :-k], np.pad(state[:, -k:], ((0, 0), (padding, padding)))), axis=1)
+
+    @staticmethod
+    def _truncate_space(state, m, keep):  # (ks/orbits.py:1541-1550)
+        k = m // 2 - 1
+        return np.concatenate((state[:, :keep], state[:, -k:][:, :keep]), axis=1)
+
     def populate(self, attr="all", **kwargs):
         if attr in ("all", "parameters"):
             self._populate_parameters(**kwargs)
@@ -434,6 +497,14 @@ class RelativeOrbitKS(OrbitKS):
     def periodic_dimensions(self):
         return (True, True) if self.frame == "comoving" else (False, True)
 
+    def _pad(self, size, axis=0, **kwargs):
+        assert self.frame == "comoving", "Mode padding requires comoving frame; set padding=False if plotting"
+        return super()._pad(size, axis=axis)
+
+    def _truncate(self, size, axis=0):
+        assert self.frame == "comoving", "Mode truncation requires comoving frame; set padding=False if plotting"
+        return super()._truncate(size, axis=axis)
+
     def populate(self, attr="all", **kwargs):
         # the reference resets S to 0 unless it estimates a shift from an existing state (ks/orbits.py:2872-2883);
         # shift estimation (calculate_spatial_shift, fsolve on the host) is outside the hot path.
@@ -443,6 +514,14 @@ class RelativeOrbitKS(OrbitKS):
 
 
 class _HalfColumnMixin:
+    @staticmethod
+    def _pad_space(state, m, size):  # one block of k columns: zeros appended (ks/orbits.py:3346-3350, :3756-3760)
+        return np.pad(state, ((0, 0), (0, (size - m) // 2)))
+
+    @staticmethod
+    def _truncate_space(state, m, keep):  # (ks/orbits.py:3391-3394, :3801-3804)
+        return state[:, :keep]
+
     def _mode_discretization(self, shape):
         return shape[0] + 1, 2 * shape[1] + 2
 

@@ -218,6 +218,23 @@ def test_continuation_matches_reference_family():
     assert relerr(S[0], g["up/modes"]) < 1e-6 and relerr(S[1], g["down/modes"]) < 1e-6 and np.array_equal(S[2], g["start/modes"])
 
 
+def test_discretization_continuation_matches_reference():
+    """discretization_continuation (reference continuation.py:170-279) with resize on the host classes and hunt on the
+    device: the stored rpo taken from 32x32 to 32x36, as the unmodified reference does it."""
+    import os
+
+    from orbithunter_b200 import RelativeOrbitKS
+    from orbithunter_b200.continuation import discretization_continuation
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ks_continuation.npz"))
+    o = RelativeOrbitKS(state=g["start/modes"], basis="modes", parameters=tuple(g["start/params"]))
+    r = discretization_continuation(o, (32, 36), methods="gmres", maxiter=40, tol=1e-6,
+                                    scipy_kwargs={"restart": 50, "maxiter": 4, "rtol": 1e-8})
+    assert r.status == int(g["disc/status"]) == 1 and tuple(r.orbit.discretization) == tuple(g["disc/shape"]) == (32, 36)
+    assert np.allclose(r.orbit.parameters, g["disc/params"], rtol=1e-7) and relerr(r.orbit.state, g["disc/modes"]) < 1e-6
+    assert r.orbit.cost() < 1e-6
+
+
 def test_device_seed_generator(gold_eval):
     """BatchedOrbitKS.from_seeds (ks_populate_state, MT19937 + legacy randn on the device) against the
     reference generator's outputs in tests/golden and the oracle, incl. sizes where the reference's integer truncation of

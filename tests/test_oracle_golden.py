@@ -207,3 +207,24 @@ def test_product_host_populate_matches_reference_generator(gold_eval):
         for (n, m) in ((16, 24), (26, 34), (34, 26), (64, 64)):
             o = CLASSES[CLASS_NAMES[cid]](parameters=(44.0, 33.4, 0.0)).populate(attr="state", seed=11, discretization=(n, m))
             assert relerr(o.state, ko.populate_state(44.0, 33.4, n, m, 11, cid)) < 1e-14
+
+
+def test_product_host_resize_matches_reference():
+    """OrbitKS.resize / _pad / _truncate of the product's host classes in the modes basis (pure NumPy, no GPU) against the
+    unmodified reference's outputs (tests/golden/ks_continuation.npz, oracle/make_golden_continuation.py)."""
+    import os
+
+    from orbithunter_b200.batch import CLASS_NAMES
+    from orbithunter_b200.ks import CLASSES
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ks_continuation.npz"))
+    for cid in range(4):
+        o = CLASSES[CLASS_NAMES[cid]](state=g[f"resize/{cid}/modes"], basis="modes", parameters=(44.0, 44.0, 0.0))
+        assert o.discretization == (16, 24)
+        for shape in ((16, 24), (20, 24), (16, 30), (12, 20), (24, 16), (32, 32)):
+            r = o.resize(*shape)
+            want = g[f"resize/{cid}/{shape[0]}x{shape[1]}"]
+            assert r.discretization == shape and r.basis == "modes" and r.state.shape == want.shape
+            assert np.array_equal(r.state, want), (cid, shape)
+        with pytest.raises(ValueError):
+            o.resize(16, 25)
