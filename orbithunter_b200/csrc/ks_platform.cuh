@@ -43,4 +43,25 @@ inline cudaError_t ks_launch_cluster(void (*kernel)(KArgs...), unsigned grid, un
 }
 #define KS_LAUNCH_CLUSTER(kernel, grid, block, cluster, smem, stream, ...) \
   ks_launch_cluster(kernel, grid, block, cluster, smem, stream, __VA_ARGS__)
+// programmatic dependent launch (sm_90+): the launch processing and CTA scheduling of a kernel overlap the tail of the
+// previous kernel in the stream; the kernel itself waits (ks_pdl_wait) before it touches global memory, so stream order
+// is preserved.
+__device__ __forceinline__ void ks_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ks_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <class... KArgs, class... Args>
+inline cudaError_t ks_launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define KS_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) ks_launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__)
 #endif

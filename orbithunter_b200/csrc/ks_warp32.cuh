@@ -316,7 +316,9 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
   double2* xcol = xb + o * 480 + kk;
   double2* xrow_a = xb + o * 480 + l16 * 15;
   double2* xrow_b = xb + o * 480 + (l16 + 16) * 15;
-  const int gw = blockIdx.x * kWarpsPerCta + warp, nw = gridDim.x * kWarpsPerCta;
+  // warp-major numbering of the persistent warps: consecutive orbits go to different SMs, so the last (partial) round of
+  // a batch is spread over all SMs with few warps each instead of filling some SMs and leaving the others idle
+  const int gw = warp * gridDim.x + blockIdx.x, nw = gridDim.x * kWarpsPerCta;
   const int npairs = (a.batch + 1) >> 1;
   const bool fix_t = a.cmask & KS_FIX_T, fix_x = a.cmask & KS_FIX_X, fix_s = (a.cmask & KS_FIX_S) || !REL;
   // does this op need N(u,u) = 1/2 Dx FFT2(u^2)?  eqn/costgrad always; matvec/rmatvec only for the dF/dL column.

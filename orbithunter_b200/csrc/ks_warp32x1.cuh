@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
   // which half-tuples exist for this lane: even / odd time index (class projection)
   const bool presE = FULL || (CLS == KS_ANTISYMMETRIC ? h == 1 : h == 1);
   const bool presO = FULL || (CLS == KS_ANTISYMMETRIC ? h == 1 : h == 0);
-  const int gw = blockIdx.x * kWarpsPerCta + warp, nw = gridDim.x * kWarpsPerCta;
+  // warp-major numbering of the persistent warps: consecutive orbits go to different SMs, so the last (partial) round of
+  // a batch is spread over all SMs with few warps each instead of filling some SMs and leaving the others idle
+  const int gw = warp * gridDim.x + blockIdx.x, nw = gridDim.x * kWarpsPerCta;
   const bool fix_t = a.cmask & KS_FIX_T, fix_x = a.cmask & KS_FIX_X, fix_s = (a.cmask & KS_FIX_S) || !REL;
   constexpr double cN = 0.5 / (64.0 * 4096.0), cP = 1.0 / (64.0 * 4096.0);
   // column offset of this lane's half inside a modes row: full classes [Re_x | Im_x], half classes a single block
@@ -219,6 +221,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
     }
     ksw32::cp_async_commit();
   };
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; nothing below may run before
+  // that kernel's writes are visible
+  ks_pdl_launch_dependents();
+  ks_pdl_wait();
   Pending next{0, 0, 0.0, 1.0, 1.0, 0.0};
   if constexpr (!ADJM) {
     next = decide(gw);

@@ -222,5 +222,9 @@ static inline T* ks_cluster_map(T* p, unsigned rank) {
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 #define KS_LAUNCH(kernel, grid, block, smem, stream, ...) ks_emul::launch(kernel, dim3(grid), dim3(block), smem, __VA_ARGS__)
+static inline void ks_pdl_wait() {}
+static inline void ks_pdl_launch_dependents() {}
+#define KS_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) \
+  (ks_emul::launch(kernel, dim3(grid), dim3(block), smem, __VA_ARGS__), cudaSuccess)
 #define KS_LAUNCH_CLUSTER(kernel, grid, block, cluster, smem, stream, ...) \
   (ks_emul::launch_cluster(kernel, grid, block, cluster, smem, __VA_ARGS__), cudaSuccess)
