@@ -262,3 +262,37 @@ def test_device_seed_generator(gold_eval):
     assert relerr(b.cpu_state(), host) < 1e-13
     with pytest.raises(ValueError):
         BatchedOrbitKS.from_seeds([-1], (44.0, 33.4, 0.0))
+
+
+def test_gluing_matches_reference():
+    """glue / tile / aspect_ratio_correction (reference gluing.py:16-302) against the unmodified reference's
+    outputs (tests/golden/ks_gluing.npz, oracle/make_golden_gluing.py): plain and strip-wise gluing in time, space and on a
+    2x2 grid, tiles of different sizes, and a symbol-array tiling."""
+    import os
+
+    from orbithunter_b200 import OrbitKS
+    from orbithunter_b200.gluing import glue, tile
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ks_gluing.npz"))
+    o = {t: OrbitKS(state=g[f"in/{t}/field"], basis="field", parameters=tuple(g[f"in/{t}/params"])) for t in "abc"}
+
+    def arr(rows):
+        x = np.empty((len(rows), len(rows[0])), dtype=object)
+        for i, r in enumerate(rows):
+            for j, v in enumerate(r):
+                x[i, j] = v
+        return x
+
+    a, b, c = o["a"], o["b"], o["c"]
+    cases = {"time": (arr([[a], [b]]), {}), "space": (arr([[a, b]]), {}), "time_strip": (arr([[a], [b]]), {"strip_wise": True}),
+             "space_strip": (arr([[a, b]]), {"strip_wise": True}), "grid_strip": (arr([[a, b], [b, a]]), {"strip_wise": True}),
+             "mixed_strip": (arr([[a], [c]]), {"strip_wise": True})}
+    for tag, (oa, kw) in cases.items():
+        r = glue(oa, OrbitKS, **kw)
+        assert tuple(r.discretization) == tuple(g[tag + "/shape"]), tag
+        assert np.allclose(r.parameters, g[tag + "/params"], rtol=1e-14), tag
+        assert relerr(r.transform(to="field").state, g[tag + "/field"]) < 1e-13, tag
+    t = tile(np.array([[0, 1], [1, 1]]), {0: a, 1: b}, OrbitKS, strip_wise=True)
+    assert np.allclose(t.parameters, g["tile/params"], rtol=1e-14) and relerr(t.transform(to="field").state, g["tile/field"]) < 1e-13
+    # the glued orbit is a usable initial condition on the device path
+    assert t.transform(to="modes").cost() > 0.0
