@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--sets", type=int, default=4, help="distinct input/output sets rotated to exceed L2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hunt", action="store_true")
+    ap.add_argument("--e2e-streams", type=int, default=2, help="streams (each with its own pinned buffers) of the e2e loop")
     ap.add_argument("--no-side", action="store_true", help="skip the side measurements (other BASELINE shapes, hybrid hunt)")
     ap.add_argument("--hunt-maxiter", type=int, default=10000)
     ap.add_argument("--variant", type=int, default=None, help="tuning: warp32 kernel variant (ks_debug_warp32_variant)")
@@ -262,7 +263,7 @@ def main():
         ms = ev0.elapsed_time(ev1)
         # ---- end-to-end through the public API from pinned host buffers: every step uploads its inputs and reads its
         # results back; two streams with their own pinned buffers so step i+1's H2D overlaps step i's D2H (PCIe is duplex)
-        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.e2e_streams))]
         hbuf = []
         for _ in streams:
             hbuf.append({"m": torch.as_tensor(base).pin_memory(), "p": torch.as_tensor(params_h).pin_memory(),
@@ -271,7 +272,7 @@ def main():
                          "c": torch.empty(BATCH, dtype=torch.float64).pin_memory()})
 
         def e2e_step(i):
-            sidx = i % 2
+            sidx = i % len(streams)
             h = hbuf[sidx]
             with torch.cuda.stream(streams[sidx]):
                 orb = BatchedOrbitKS(h["m"].to(dev, non_blocking=True), h["p"].to(dev, non_blocking=True), "OrbitKS", "modes")
@@ -287,10 +288,12 @@ def main():
         t_e0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(streams[0])
-        streams[1].wait_event(e0)
+        for st_ in streams[1:]:
+            st_.wait_event(e0)
         for i in range(e2e_steps):
             e2e_step(i)
-        streams[0].wait_stream(streams[1])
+        for st_ in streams[1:]:
+            streams[0].wait_stream(st_)
         e1.record(streams[0])
         barrier()
         e2e_ms = e0.elapsed_time(e1)

@@ -41,7 +41,9 @@ int launch_warp32_as_pc(const KsEvalArgs& a, cudaStream_t s) {
       return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(warp32 async) failed");
     attr_done = true;
   }
-  KS_LAUNCH(kern, warp32_grid(a.batch, Cfg::warps_per_cta), Cfg::warps_per_cta * 32, Cfg::smem_bytes, s, a);
+  if (KS_LAUNCH_PDL(kern, (unsigned)warp32_grid(a.batch, Cfg::warps_per_cta), (unsigned)(Cfg::warps_per_cta * 32), (size_t)Cfg::smem_bytes,
+                    s, a) != cudaSuccess)
+    return fail(KS_ERR_LAUNCH, "warp32 async kernel launch failed");
   return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32 async kernel launch failed");
 }
 template <int CLS, int OP>

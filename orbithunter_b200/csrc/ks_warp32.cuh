@@ -324,6 +324,9 @@ __global__ void __launch_bounds__(Cfg<TS>::warps_per_cta * 32, 1) ks_warp32_kern
   // does this op need N(u,u) = 1/2 Dx FFT2(u^2)?  eqn/costgrad always; matvec/rmatvec only for the dF/dL column.
   const bool need_nuu = (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) || !fix_x;
 
+  // programmatic dependent launch: the set-up above overlapped the previous kernel's tail; no global access before this
+  ks_pdl_launch_dependents();
+  ks_pdl_wait();
   if constexpr (AS) {  // stage the first pair's u modes into the (still unused) field stash
     if (gw < npairs) {
       const int ob0 = (2 * gw + o < a.batch) ? 2 * gw + o : a.batch - 1;
