@@ -39,13 +39,15 @@ def basis_shape(cls_id, n, m, basis):
 _WORKSPACES = {}
 
 
-def workspace(device, nbytes):
+def workspace(device, nbytes, stream=None):
     """Scratch buffer per (device, current stream), grown on demand (sized by *_workspace_bytes); never shrinks."""
-    dev = torch.device(device)
-    key = (dev.index or 0, torch.cuda.current_stream(dev).cuda_stream)
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    if stream is None:
+        stream = torch.cuda.current_stream(dev).cuda_stream
+    key = (dev.index or 0, stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+        ws = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=dev)
         _WORKSPACES[key] = ws
     return ws
 
@@ -148,18 +150,32 @@ class BatchedOrbitKS:
         return self.batch
 
     def _like(self, state=None, parameters=None, basis=None):
-        return BatchedOrbitKS(self.state if state is None else state, self.parameters if parameters is None else parameters,
-                              self.cls_id, self.basis if basis is None else basis, self.discretization, self.constraints)
+        """Another batch of the same class / grid / constraints around freshly computed tensors (no re-validation: the
+        callers pass float64 contiguous CUDA tensors of the right shapes)."""
+        out = object.__new__(BatchedOrbitKS)
+        out.cls_id = self.cls_id
+        out.state = self.state if state is None else state
+        out.parameters = self.parameters if parameters is None else parameters
+        out.basis = self.basis if basis is None else basis
+        out.discretization = self.discretization
+        out.constraints = dict(self.constraints)
+        return out
 
     def copy(self):
         return self._like(self.state.clone(), self.parameters.clone())
 
     def _call(self, fn, *args):
         L = _lib.lib()
+        dev = self.state.device
         nbytes = L.ks_workspace_bytes(self.cls_id, self.n, self.m, self.batch)
-        ws = workspace(self.state.device, nbytes)
-        with torch.cuda.device(self.state.device):
-            stream = torch.cuda.current_stream().cuda_stream
+        if torch.cuda.current_device() == dev.index:  # the common case: no device switch, one stream lookup
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            ws = workspace(dev, nbytes, stream)
+            _lib.check(getattr(L, fn)(self.cls_id, self.n, self.m, self.batch, *args, ws.data_ptr(), ws.numel(), stream))
+            return
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            ws = workspace(dev, nbytes, stream)
             _lib.check(getattr(L, fn)(self.cls_id, self.n, self.m, self.batch, *args, ws.data_ptr(), ws.numel(), stream))
 
     def _need_modes(self):
