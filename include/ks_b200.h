@@ -40,7 +40,8 @@ void ks_debug_force_generic(int on);
  * (all ops); 4 (default) = one orbit per warp, 8 warps/SM, all state in registers (eqn and costgrad; other ops use 3). */
 void ks_debug_warp32_variant(int variant);
 /* tuning hook, large-grid (n, m in {64, 128, 256}) tile path: enabled = 0 routes those shapes through the generic
- * kernel (cross-check); chunk_mb > 0 sets the workspace budget that bounds how many orbits one pass sequence covers. */
+ * kernel (cross-check), 1 (default) = tile path with the CTA-resident fused kernel at 64x64, 2 = multi-pass tiles for
+ * every shape; chunk_mb > 0 sets the workspace budget that bounds how many orbits one pass sequence covers. */
 void ks_debug_tile(int enabled, int chunk_mb);
 /* tuning / test hook, 32x32 adjoint descent: passes every orbit runs inside one launch of the multi-pass kernel with its
  * state on chip (default 128); 0 = the one-pass-per-launch kernel with the state in global memory (cross-check). */

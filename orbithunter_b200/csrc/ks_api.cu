@@ -105,9 +105,9 @@ int launch_generic(const ksg::GenArgs& ga, cudaStream_t s) {
 // unit, compiled in parallel); see ks_tile_host.cuh ----
 int g_adj_inner = 128;  // 32x32 adjoint descent: passes per launch of the multi-pass kernel (0 = one pass per launch)
 int g_gmres_cluster = 1;  // 0 = one CTA per orbit GMRES step (cross-check), 1 = auto cluster size, 2/4/8 = at least that size
-bool g_tile_enabled = true;
+int g_tile_mode = 1;  // 0 = generic kernel, 1 = tile path with the CTA-resident 64x64 kernel, 2 = tile path, multi-pass only
 int g_tile_chunk_mb = 256;
-bool use_tile(int n, int m) { return g_tile_enabled && !g_force_generic && kst::size_ok(n) && kst::size_ok(m); }
+bool use_tile(int n, int m) { return g_tile_mode != 0 && !g_force_generic && kst::size_ok(n) && kst::size_ok(m); }
 int tile_chunk(int n, int m, int cols, int batch) {
   const size_t per = kst::orbit_doubles(n, m, cols) * 8;
   size_t c = ((size_t)g_tile_chunk_mb << 20) / per;
@@ -119,7 +119,8 @@ size_t tile_workspace_bytes(int n, int m, int cols, int batch) {
 }
 template <int OP>
 int launch_tile(int cls, int n, int m, const KsEvalArgs& a, cudaStream_t s) {
-  const int chunk = tile_chunk(n, m, mode_cols(cls, m), a.batch);
+  // 64x64: the CTA-resident fused kernel (chunk < 0 selects it); everything else: the multi-pass tiles
+  const int chunk = (n == 64 && m == 64 && g_tile_mode == 1) ? -1 : tile_chunk(n, m, mode_cols(cls, m), a.batch);
   switch (cls) {
     case KS_ORBIT: return ks_tile_run_c0(OP, n, m, chunk, a, s);
     case KS_RELATIVE: return ks_tile_run_c1(OP, n, m, chunk, a, s);
@@ -176,7 +177,7 @@ void ks_debug_force_generic(int on) { g_force_generic = on != 0; }
 void ks_debug_adjoint_inner(int passes) { g_adj_inner = passes < 0 ? 0 : passes; }
 void ks_debug_gmres_cluster(int mode) { g_gmres_cluster = (mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8) ? mode : 1; }
 void ks_debug_tile(int enabled, int chunk_mb) {
-  g_tile_enabled = enabled != 0;
+  g_tile_mode = (enabled == 0 || enabled == 2) ? enabled : 1;
   if (chunk_mb > 0) g_tile_chunk_mb = chunk_mb;
 }
 void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant == 3 || variant == 4) ? variant : 4; }

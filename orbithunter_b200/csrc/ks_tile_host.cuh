@@ -5,6 +5,7 @@
 
 #include "ks_host.cuh"
 #include "ks_tile.cuh"
+#include "ks_tile64.cuh"
 
 #ifndef KS_TILE_CLS
 #error "define KS_TILE_CLS (0..3) before including ks_tile_host.cuh"
@@ -80,9 +81,29 @@ int tile_chunk_run(kst::TileArgs& ta, cudaStream_t s) {
   }
   return 0;
 }
+// 64x64: one CTA per orbit, all passes on chip (ks_tile64.cuh); `chunk` < 0 selects it
+template <int CLS, int OP>
+int launch_fused64(const KsEvalArgs& a, cudaStream_t s) {
+  auto kern = kst::tile_fused64_kernel<CLS, OP>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kst::F64::smem_bytes) != cudaSuccess)
+      return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(fused64) failed");
+    attr_done = true;
+  }
+  kst::TileArgs ta;
+  std::memset(&ta, 0, sizeof(ta));
+  ta.e = a;
+  ta.g = make_geom(CLS, 64, 64);
+  ta.TU = a.scratch;  // one stage-1 slot (Nm doubles) per CTA
+  const int cap = 2 * sm_count();
+  KS_LAUNCH(kern, a.batch < cap ? a.batch : cap, kst::kF64Threads, kst::F64::smem_bytes, s, ta);
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "fused 64x64 kernel launch failed");
+}
 template <int CLS, int OP>
 int launch_tile(int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s) {
   if (int rc = tile_ensure_twiddles(s)) return rc;
+  if (chunk < 0) return launch_fused64<CLS, OP>(a, s);
   const kspw::Geom g = make_geom(CLS, n, m);
   const int KB = kst::col_lines(n), TB = kst::col_lines(m);
   const int nkb = (g.k + KB - 1) / KB, ntb = (n / 2) / TB;

@@ -78,13 +78,23 @@ def test_tile_kernels_all_ops(cid, shape):
     """Large-grid multi-pass path (ks_tile.cuh): every pass kernel, every radix plan (64 = 8x8, 128 = 16x8, 256 = 16x16)."""
     L = E.lib()
     L.ks_debug_force_generic(0)
-    L.ks_debug_tile(1, 1 if shape == (64, 64) else 64)  # 1 MB budget: the 3-orbit batch runs as several chunks
+    L.ks_debug_tile(2, 1 if shape == (64, 64) else 64)  # multi-pass tiles; 1 MB budget: the 3-orbit batch runs as several chunks
     try:
         cons_list = (ko.default_constraints(cid), (True, True, True)) if shape == (64, 64) else (ko.default_constraints(cid),)
         for cons in cons_list:
             _check_all_ops(cid, shape[0], shape[1], 3, cons)
     finally:
         L.ks_debug_tile(1, 64)
+
+
+@pytest.mark.parametrize("cid", range(4))
+def test_fused64_kernel_all_ops(cid):
+    """CTA-resident 64x64 kernel (ks_tile64.cuh): all ops, more orbits than resident CTAs (persistent loop)."""
+    L = E.lib()
+    L.ks_debug_force_generic(0)
+    L.ks_debug_tile(1, 64)
+    for cons in (ko.default_constraints(cid), (True, True, True)):
+        _check_all_ops(cid, 64, 64, 3 if cons[1] else 11, cons)
 
 
 @pytest.mark.parametrize("cid", range(4))

@@ -177,17 +177,19 @@ def test_tile_matches_generic_kernel(cid, shape, B):
                 r.cpu_parameters(), u.eqn().cpu_state()]
 
     try:
-        L.ks_debug_tile(1, 2)  # 2 MB workspace budget: 1 .. 20 orbits per chunk
+        L.ks_debug_tile(2, 2)  # multi-pass tiles, 2 MB workspace budget: 1 .. 20 orbits per chunk
         small = run()
-        L.ks_debug_tile(1, 64)
+        L.ks_debug_tile(2, 256)
         big = run()
+        L.ks_debug_tile(1, 256)  # default: at 64x64 the CTA-resident fused kernel (ks_tile64.cuh), else the same tiles
+        dflt = run()
         L.ks_debug_tile(0, 0)
         ref = run()
     finally:
-        L.ks_debug_tile(1, 64)
-    for x, y, z in zip(small, big, ref):
+        L.ks_debug_tile(1, 256)
+    for x, y, d, z in zip(small, big, dflt, ref):
         assert np.array_equal(x, y)  # chunking does not change a single bit
-        assert relerr(x, z) < _tol(M[0], cid, 44.0)
+        assert relerr(x, z) < _tol(M[0], cid, 44.0) and relerr(d, z) < _tol(M[0], cid, 44.0)
 
 
 @pytest.mark.parametrize("cid", range(4))
