@@ -181,7 +181,9 @@ def side_shapes(peak_gbs):
         nm = M.shape[1] * M.shape[2]
         gbs = B * 8 * (2 * nm + 7) / ms / 1e6
         out.append({"class": cls, "grid": [n, m], "batch": B, "evals_per_s": B / ms * 1e3, "algorithmic_GBps": gbs,
-                    "hbm_frac": gbs / peak_gbs, "kernels": "ks_tile.cuh: 5 line-block passes per evaluation"})
+                    "hbm_frac": gbs / peak_gbs,
+                    "kernels": ("ks_tile64.cuh: one CTA per orbit, all passes in shared memory" if (n, m) == (64, 64)
+                                else "ks_tile.cuh: 5 line-block passes per evaluation")})
     return out
 
 
