@@ -735,7 +735,9 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
       // GMRES step: vectors longer than 8192 are split over a cluster of 2 / 4 / 8 CTAs per orbit, each holding its slice
       // in registers; shorter ones (and N > 65536, and the debug switch) use the one-CTA-per-orbit kernel
       int gm_cluster = 0;
-      if (g_gmres_cluster > 1 || (g_gmres_cluster == 1 && N > kskry::kSlice)) {  // short vectors: one CTA per orbit is faster
+      // mode 1 (auto): register-resident vector for N <= 4096 (one CTA, 8 or 16 elements per thread) and N > 8192 (clusters);
+      // in between (and mode 0) the basis-in-memory kernel
+      if (g_gmres_cluster > 1 || (g_gmres_cluster == 1 && (N > kskry::kSlice || N <= 16 * kskry::kThreads))) {
         gm_cluster = g_gmres_cluster;
         while (gm_cluster < kskry::kMaxCluster && (size_t)gm_cluster * kskry::kSlice < (size_t)N) gm_cluster *= 2;
         if ((size_t)gm_cluster * kskry::kSlice < (size_t)N) gm_cluster = 0;
@@ -751,9 +753,17 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
         if ((rc = op_rmatvec(Fy, wout)) != 0) return rc;
         cudaMemsetAsync(counters, 0, 4, s);
         if (gm_cluster > 0) {
-          if (KS_LAUNCH_CLUSTER(kskry::gmres_step_cluster_kernel, (unsigned)batch * gm_cluster, (unsigned)kskry::kThreads,
-                                (unsigned)gm_cluster, (size_t)kskry::kClusterSmemBytes, s, g) != cudaSuccess)
-            return fail(KS_ERR_LAUNCH, "newton-krylov: cluster launch of the GMRES step failed");
+          cudaError_t ce;
+          if (gm_cluster == 1 && N <= 8 * kskry::kThreads)
+            ce = KS_LAUNCH_CLUSTER(kskry::gmres_step_cluster_kernel<8>, (unsigned)batch, (unsigned)kskry::kThreads, 1u,
+                                   (size_t)kskry::kClusterSmemBytes, s, g);
+          else if (gm_cluster == 1 && N <= 16 * kskry::kThreads)
+            ce = KS_LAUNCH_CLUSTER(kskry::gmres_step_cluster_kernel<16>, (unsigned)batch, (unsigned)kskry::kThreads, 1u,
+                                   (size_t)kskry::kClusterSmemBytes, s, g);
+          else
+            ce = KS_LAUNCH_CLUSTER(kskry::gmres_step_cluster_kernel<32>, (unsigned)batch * gm_cluster, (unsigned)kskry::kThreads,
+                                   (unsigned)gm_cluster, (size_t)kskry::kClusterSmemBytes, s, g);
+          if (ce != cudaSuccess) return fail(KS_ERR_LAUNCH, "newton-krylov: cluster launch of the GMRES step failed");
         } else {
           KS_LAUNCH(kskry::gmres_step_kernel, batch, kskry::kThreads, 0, s, g);
         }

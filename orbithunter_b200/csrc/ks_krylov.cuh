@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kThreads) gmres_step_kernel(const GmresState g
 // All shared memory is dynamic (the CPU emulation runs the blocks of a cluster concurrently).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSliceRegs = 32;
-constexpr int kSlice = kThreads * kSliceRegs;  // 8192 elements per CTA
+constexpr int kSlice = kThreads * kSliceRegs;  // 8192 elements per CTA (clusters); short vectors use 8 or 16 registers per thread
 constexpr int kMaxCluster = 8;
 constexpr int kClusterSmemBytes = (kThreads / 32 + 2 * 2 + 2) * 8 + 16;
 
@@ -343,7 +343,9 @@ KS_DEVI double cluster_sum(double v, ClusterRed& cr) {
   return tot;
 }
 
+template <int SR>  // vector elements per thread: 32 (clusters, N > 8192), 16 (N <= 4096) or 8 (N <= 2048) for one-CTA "clusters"
 __global__ void __launch_bounds__(kThreads) gmres_step_cluster_kernel(const GmresState g) {
+  constexpr int kSliceRegs = SR;
   KS_DYN_SMEM(double, dsm);
   ClusterRed cr;
   cr.sh = dsm;

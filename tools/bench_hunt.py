@@ -1,5 +1,5 @@
 """Side measurements of the Newton-Krylov hunts at BASELINE configs 3 and 4 (bounded): wall time, outcome counts.
-python tools/bench_hunt.py [cfg3|cfg4|all] [B3] [B4]"""
+python tools/bench_hunt.py [cfg3|cfg4|all] [B3] [B4] [gmres_cluster_mode]"""
 import json
 import os
 import sys
@@ -31,6 +31,9 @@ def run(tag, fn):
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 B3 = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 B4 = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+if len(sys.argv) > 4:  # GMRES step kernel selection (ks_debug_gmres_cluster)
+    from orbithunter_b200 import _lib
+    _lib.lib().ks_debug_gmres_cluster(int(sys.argv[4]))
 if which in ("cfg3", "all"):
     for cls in ("ShiftReflectionOrbitKS", "AntisymmetricOrbitKS", "RelativeOrbitKS"):
         u = BatchedOrbitKS(seeds(cls, 64, 64, 60.0, 44.0, B3), np.tile([60.0, 44.0, 0.0], (B3, 1)), cls)
