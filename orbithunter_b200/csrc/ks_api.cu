@@ -19,7 +19,8 @@ bool shape_ok(int cls, int n, int m) {
   return cls >= 0 && cls <= 3 && n >= 4 && m >= 4 && (n % 2 == 0) && (m % 2 == 0) && n <= 4096 && m <= 4096;
 }
 bool g_force_generic = false;  // debug/test switch: route 32x32 through the generic kernel as a cross-check
-int g_warp32_variant = 4;  // 3: two orbits per warp, cp.async staging (all ops); 4: one orbit per warp, register-resident (eqn, costgrad)  // which warp32 build variant to launch (see ks_warp32.cuh Cfg)
+int g_warp32_variant = 4;  // 32x32 eqn / costgrad / adjoint descent: 4 = one orbit per warp (ks_warp32x1.cuh, default), 3 = two orbits per
+                           // warp (ks_warp32.cuh, which always serves matvec / rmatvec)
 bool use_warp32(int n, int m) { return n == 32 && m == 32 && !g_force_generic; }
 int warp32_grid(int batch, int warps_per_cta) {
   const int npairs = (batch + 1) / 2;

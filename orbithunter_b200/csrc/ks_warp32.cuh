@@ -30,6 +30,9 @@ using ks::static_for;
 //               through an L2-resident global scratch slot and the u modes are re-read from global in phase C.
 //   TS = true : + a lane-private tuple stash (16 KB) holding u's tuples from phase A to C and F from C to E
 //               -> 4 warps / SM, but no global/L2 round trips inside an evaluation.
+// The library instantiates TS = false with AS = true (all global reads staged with cp.async one transform ahead), for
+// matvec / rmatvec and as the cross-check of ks_warp32x1.cuh; the other combinations are kept for the measurements in
+// DESIGN.md section 4 (profiles/r01b, r01e).
 constexpr int kXbDoubles = 2 * 480 * 2, kSuDoubles = 2 * 1024, kTsDoubles = 2 * 1024;
 template <bool TS>
 struct Cfg {
