@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
     objs, procs = [], []
     for src in sources():  # one nvcc per translation unit, all at once
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "-I", CSRC, "-I", INCLUDE, "-c", src,
+        cmd = [NVCC, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-diag-suppress", "128,177", "-Xcompiler", "-fPIC", "-I", CSRC, "-I", INCLUDE, "-c", src,
                "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -66,8 +66,12 @@ int launch_warp32x1_pc(const KsEvalArgs& a, cudaStream_t s) {
   }
   const int ctas = (a.batch + ksx1::kWarpsPerCta - 1) / ksx1::kWarpsPerCta;
   const int sms = sm_count();
-  if (KS_LAUNCH_PDL(kern, (unsigned)(ctas < sms ? ctas : sms), (unsigned)(ksx1::kWarpsPerCta * 32), (size_t)smem, s, a) != cudaSuccess)
-    return fail(KS_ERR_LAUNCH, "warp32x1 kernel launch failed");
+  const cudaError_t ce = KS_LAUNCH_PDL(kern, (unsigned)(ctas < sms ? ctas : sms), (unsigned)(ksx1::kWarpsPerCta * 32), (size_t)smem, s, a);
+  if (ce != cudaSuccess) {
+    static char msg[160];
+    std::snprintf(msg, sizeof(msg), "warp32x1 kernel launch failed: %s", cudaGetErrorString(ce));
+    return fail(KS_ERR_LAUNCH, msg);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32x1 kernel launch failed");
 }
 template <int CLS>
