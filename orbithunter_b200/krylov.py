@@ -1,4 +1,4 @@
-"""Newton-Krylov methods of hunt() on the device: 'gmres', 'lsqr' and the matrix-free 'newton_descent'.
+"""Newton-Krylov methods of hunt() on the device: 'gmres', 'lsqr' and the matrix-free 'newton_descent' / 'lstsq'.
 
 Reference: orbithunter/optimize.py _scipy_sparse_linalg_solver_wrapper :1196-1404 (+ _sparse_linalg_factory :1682-1850)
 and _newton_descent :653-852.  ``scipy_kwargs`` keeps SciPy's names: gmres -> restart, maxiter (restart cycles), rtol,
@@ -44,7 +44,10 @@ def newton_krylov(orb: BatchedOrbitKS, method="gmres", tol=1e-6, ftol=1e-9, maxi
         inner = 2 * N if inner is None else int(inner)
         rtol, atol, btol, conlim = 0.0, float(sk.pop("atol", 1e-6)), float(sk.pop("btol", 1e-6)), float(sk.pop("conlim", 1e8))
         preconditioning = False  # the reference never preconditions lsqr/lsmr (optimize.py:1317-1321)
-    elif method == "newton_descent":
+    elif method in ("newton_descent", "lstsq"):
+        if method == "lstsq" and preconditioning:
+            raise NotImplementedError("hunt('lstsq', preconditioning=True) (dense right-preconditioned least squares) is not "
+                                      "provided on the device path; use preconditioning=False")
         # dx = pinv(J) (-F): the minimum-norm least-squares step, which LSQR from x0 = 0 converges to.  Stated
         # tolerance of the restatement: atol = btol = 1e-13, up to 4 N Golub-Kahan steps, no condition limit.
         mid, restart, preconditioning = 1, 1, False

@@ -2,8 +2,10 @@
 
 Methods on the device path: 'adj' (adjoint descent, optimize.py:367-509), 'gmres' and 'lsqr' (Newton-Krylov,
 optimize.py:1196-1404 with _sparse_linalg_factory :1682-1850), 'newton_descent' (matrix-free restatement of
-:653-852: the pseudo-inverse step -J^+ F is the minimum-norm least-squares solution LSQR converges to from x0 = 0).
-Everything else the reference offers (the SciPy minimize/root pass-throughs, dense lstsq/solve) is outside the
+:653-852: the pseudo-inverse step -J^+ F is the minimum-norm least-squares solution LSQR converges to from x0 = 0) and
+'lstsq' (:855-1022, without preconditioning: scipy.linalg.lstsq returns the same minimum-norm step and the outer loop is
+the same, so it runs on the same matrix-free path; this is the second stage of BASELINE configs[0]).
+Everything else the reference offers (the SciPy minimize/root pass-throughs, dense solve, preconditioned lstsq) is outside the
 north star's path and raises NotImplementedError here.
 
 Keyword handling follows the reference: tol / ftol / maxiter / min_step / preconditioning may be scalars or
@@ -23,7 +25,7 @@ from .ks import OrbitKS
 
 __all__ = ["hunt", "OrbitResult"]
 
-_DEVICE_METHODS = ("adj", "gmres", "lsqr", "newton_descent")
+_DEVICE_METHODS = ("adj", "gmres", "lsqr", "newton_descent", "lstsq")
 _MESSAGES = {
     -1: "Has not failed yet: tolerance not met but no exit condition triggered.",
     0: "Failed to converge: minimum backtracking step size reached.",
@@ -98,7 +100,7 @@ def _adjoint_descent(orb: BatchedOrbitKS, tol=1e-6, ftol=1e-9, maxiter=10000, mi
 def _run_method(orb, method, hunt_kwargs):
     if method == "adj":
         return _adjoint_descent(orb, **hunt_kwargs)
-    if method in ("gmres", "lsqr", "newton_descent"):
+    if method in ("gmres", "lsqr", "newton_descent", "lstsq"):
         from .krylov import newton_krylov
 
         return newton_krylov(orb, method=method, **hunt_kwargs)

@@ -296,3 +296,30 @@ def test_gluing_matches_reference():
     assert np.allclose(t.parameters, g["tile/params"], rtol=1e-14) and relerr(t.transform(to="field").state, g["tile/field"]) < 1e-13
     # the glued orbit is a usable initial condition on the device path
     assert t.transform(to="modes").cost() > 0.0
+
+
+def test_lstsq_matches_reference():
+    """hunt('lstsq') (reference optimize.py:855-1022, the second stage of BASELINE configs[0]) on the matrix-free path: the
+    reference's dense scipy.linalg.lstsq step is the minimum-norm least-squares solution, which the device LSQR reaches to
+    its stated 1e-13 tolerance.  Goldens from the unmodified reference (tests/golden/ks_lstsq.npz)."""
+    import os
+
+    from orbithunter_b200 import OrbitKS
+    from orbithunter_b200.optimize import hunt
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ks_lstsq.npz"))
+    o = OrbitKS(state=g["lstsq/modes"], basis="modes", parameters=tuple(g["lstsq/params"]))
+    r = hunt(o, "lstsq", maxiter=3)
+    assert (r.status, r.nit) == tuple(int(x) for x in g["lstsq/status_nit"])
+    assert abs(r.costs[-1] - g["lstsq/costs"][-1]) < 1e-6 * g["lstsq/costs"][-1]
+    assert relerr(r.orbit.state, g["lstsq/state"]) < 1e-6 and np.allclose(r.orbit.parameters, g["lstsq/out_params"], rtol=1e-7)
+    # configs[0] in miniature: adjoint descent, then lstsq
+    o2 = OrbitKS(state=g["cfg0/modes"], basis="modes", parameters=tuple(g["cfg0/params"]))
+    r2 = hunt(o2, ("adj", "lstsq"), maxiter=[300, 4], tol=[1e-6, 1e-10])
+    assert r2.status == int(g["cfg0/status"]) and list(r2.nit) == [int(x) for x in g["cfg0/nit"]]
+    assert np.allclose(r2.costs, g["cfg0/costs"], rtol=1e-6)
+    assert relerr(r2.orbit.state, g["cfg0/state"]) < 1e-6
+    with pytest.raises(NotImplementedError):
+        hunt(o, "lstsq", maxiter=1, preconditioning=True)
+    with pytest.raises(NotImplementedError):
+        hunt(o, "solve", maxiter=1)
