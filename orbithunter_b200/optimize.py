@@ -3,8 +3,8 @@
 Methods on the device path: 'adj' (adjoint descent, optimize.py:367-509), 'gmres' and 'lsqr' (Newton-Krylov,
 optimize.py:1196-1404 with _sparse_linalg_factory :1682-1850), 'newton_descent' (matrix-free restatement of
 :653-852: the pseudo-inverse step -J^+ F is the minimum-norm least-squares solution LSQR converges to from x0 = 0) and
-'lstsq' (:855-1022, without preconditioning: scipy.linalg.lstsq returns the same minimum-norm step and the outer loop is
-the same, so it runs on the same matrix-free path; this is the second stage of BASELINE configs[0]).
+'lstsq' (:855-1022, without preconditioning; the second stage of BASELINE configs[0]): dense Jacobian by one batched
+matvec, minimum-norm step by an SVD pseudo-inverse on the device, orbit by orbit as the reference does.
 Everything else the reference offers (the SciPy minimize/root pass-throughs, dense solve, preconditioned lstsq) is outside the
 north star's path and raises NotImplementedError here.
 

@@ -299,9 +299,9 @@ def test_gluing_matches_reference():
 
 
 def test_lstsq_matches_reference():
-    """hunt('lstsq') (reference optimize.py:855-1022, the second stage of BASELINE configs[0]) on the matrix-free path: the
-    reference's dense scipy.linalg.lstsq step is the minimum-norm least-squares solution, which the device LSQR reaches to
-    its stated 1e-13 tolerance.  Goldens from the unmodified reference (tests/golden/ks_lstsq.npz)."""
+    """hunt('lstsq') (reference optimize.py:855-1022, the second stage of BASELINE configs[0]): dense Jacobian from the
+    device matvec, minimum-norm step from the SVD pseudo-inverse on the device, reference outer loop.  Goldens from the
+    unmodified reference (tests/golden/ks_lstsq.npz): a 16x16 seed and configs[0] in miniature (adj then lstsq at 32x32)."""
     import os
 
     from orbithunter_b200 import OrbitKS
