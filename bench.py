@@ -264,6 +264,16 @@ def main():
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
+        # the same step timed one launch at a time (best and median of >= 10 repetitions); the events between the
+        # launches keep consecutive kernels from overlapping their launch latency, so these are upper bounds of the mean above
+        n_single = max(10, min(args.steps, 50))
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_single)]
+        for i, (a0, a1) in enumerate(evs):
+            a0.record()
+            step(i)
+            a1.record()
+        torch.cuda.synchronize()
+        single = sorted(a0.elapsed_time(a1) for a0, a1 in evs)
         # ---- end-to-end through the public API from pinned host buffers: every step uploads its inputs and reads its
         # results back; two streams with their own pinned buffers so step i+1's H2D overlaps step i's D2H (PCIe is duplex)
         streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.e2e_streams))]
@@ -369,6 +379,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * (NM + 3) * 8,
                 "d2h_bytes_per_step": BATCH * (NM + 3 + 1) * 8, "steps": e2e_steps},
         "gpu_launches": args.steps, "clocks": clocks.summary(), "checksum_cost_sum": checksum,
+        "single_launch_ms": {"best": single[0], "median": single[len(single) // 2], "n": len(single)},
     }
     if hunt_stats is not None:
         line["adjoint_descent"] = hunt_stats
