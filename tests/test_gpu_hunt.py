@@ -216,6 +216,11 @@ def test_continuation_matches_reference_family():
     assert np.array_equal(P[2], g["start/params"])
     S = rb.orbit.cpu_state()
     assert relerr(S[0], g["up/modes"]) < 1e-6 and relerr(S[1], g["down/modes"]) < 1e-6 and np.array_equal(S[2], g["start/modes"])
+    # a family whose first re-convergence fails keeps its last converged member and reports the failing hunt's status
+    rf = continuation_batch(batch, "t", targets, step_size=0.02, methods="gmres", maxiter=1, tol=1e-14,
+                            scipy_kwargs={"restart": 5, "maxiter": 1, "rtol": 1e-2})
+    assert rf.status.tolist() == [2, 2, 1] and rf.reached.tolist() == [False, False, True] and rf.steps.tolist() == [0, 0, 0]
+    assert np.array_equal(rf.orbit.cpu_state(), batch.cpu_state()) and np.array_equal(rf.orbit.cpu_parameters(), batch.cpu_parameters())
 
 
 def test_discretization_continuation_matches_reference():
