@@ -162,7 +162,8 @@ def side_shapes(peak_gbs):
     from orbithunter_b200.ks import CLASSES
 
     out = []
-    for cls, n, m, T, L, B in (("RelativeOrbitKS", 64, 64, 60.0, 44.0, 4096), ("ShiftReflectionOrbitKS", 64, 64, 60.0, 44.0, 4096),
+    for cls, n, m, T, L, B in (("OrbitKS", 32, 32, T0, L0, 65536),  # configs[4] batch: 55 full rounds of the persistent warps
+                               ("RelativeOrbitKS", 64, 64, 60.0, 44.0, 4096), ("ShiftReflectionOrbitKS", 64, 64, 60.0, 44.0, 4096),
                                ("AntisymmetricOrbitKS", 64, 64, 60.0, 44.0, 4096), ("OrbitKS", 256, 256, 200.0, 200.0, 64)):
         base = np.stack([CLASSES[cls](parameters=(T, L, 0.0)).populate(attr="state", seed=s, discretization=(n, m)).state
                          for s in range(8)])
@@ -183,7 +184,9 @@ def side_shapes(peak_gbs):
         gbs = B * 8 * (2 * nm + 7) / ms / 1e6
         out.append({"class": cls, "grid": [n, m], "batch": B, "evals_per_s": B / ms * 1e3, "algorithmic_GBps": gbs,
                     "hbm_frac": gbs / peak_gbs,
-                    "kernels": ("ks_tile64.cuh: one CTA per orbit, all passes in shared memory" if (n, m) == (64, 64)
+                    "kernels": ("ks_warp32x1.cuh: one warp per orbit (the headline kernel at the 65 536-seed sweep's batch)"
+                                if (n, m) == (32, 32) else
+                                "ks_tile64.cuh: one CTA per orbit, all passes in shared memory" if (n, m) == (64, 64)
                                 else "ks_tile.cuh: 5 line-block passes per evaluation")})
     return out
 
