@@ -483,7 +483,15 @@ def newton_krylov(modes, params, cls=ORBIT, constraints=None, method="gmres", to
             b = -1.0 * eqn(modes, params, cls).ravel()
             x = lsqr(A, b, **scipy_kwargs)[0]
         else:
-            ata, atb = normal_operator(modes, params, cls, constraints)
+            if N == modes.size:
+                # square system (every parameter constrained): J dx = -F itself, optimize.py:1803-1850
+                def ata(v):
+                    vs, vp = from_cdof(np.asarray(v).ravel(), shape, constraints)
+                    return matvec(modes, params, vs, vp, cls, constraints).ravel()
+
+                atb = -1.0 * eqn(modes, params, cls).ravel()
+            else:
+                ata, atb = normal_operator(modes, params, cls, constraints)
             A = LinearOperator((N, N), matvec=ata, rmatvec=ata, dtype=float)
             kw = dict(scipy_kwargs)
             if preconditioning:

@@ -32,67 +32,14 @@ int generic_grid(int batch) {
   const int cap = 2 * sm_count();
   return batch < cap ? batch : cap;
 }
-template <int CLS, int OP, bool PC>
-int launch_warp32_as_pc(const KsEvalArgs& a, cudaStream_t s) {
-  using Cfg = ksw32::Cfg<false>;
-  auto kern = ksw32::ks_warp32_kernel<CLS, OP, false, true, PC, false>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes) != cudaSuccess)
-      return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(warp32 async) failed");
-    attr_done = true;
+// 32x32 kernels: instantiated per symmetry class in ks_w32_c{0..3}.cu (see ks_w32_host.cuh)
+int w32_run(int cls, int op, const KsEvalArgs& a, cudaStream_t s) {
+  switch (cls) {
+    case KS_ORBIT: return ks_w32_run_c0(op, g_warp32_variant, a, s);
+    case KS_RELATIVE: return ks_w32_run_c1(op, g_warp32_variant, a, s);
+    case KS_SHIFT_REFLECTION: return ks_w32_run_c2(op, g_warp32_variant, a, s);
+    default: return ks_w32_run_c3(op, g_warp32_variant, a, s);
   }
-  if (KS_LAUNCH_PDL(kern, (unsigned)warp32_grid(a.batch, Cfg::warps_per_cta), (unsigned)(Cfg::warps_per_cta * 32), (size_t)Cfg::smem_bytes,
-                    s, a) != cudaSuccess)
-    return fail(KS_ERR_LAUNCH, "warp32 async kernel launch failed");
-  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32 async kernel launch failed");
-}
-template <int CLS, int OP>
-int launch_warp32_as(const KsEvalArgs& a, cudaStream_t s) {
-  if constexpr (OP == KS_OP_COSTGRAD) {
-    if (a.precond) return launch_warp32_as_pc<CLS, OP, true>(a, s);
-  }
-  return launch_warp32_as_pc<CLS, OP, false>(a, s);
-}
-template <int CLS, int OP, bool PC>
-int launch_warp32x1_pc(const KsEvalArgs& a, cudaStream_t s) {
-  auto kern = ksx1::ks_warp32x1_kernel<CLS, OP, PC>;
-  constexpr int smem = ksx1::smem_bytes(OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(warp32x1) failed");
-    attr_done = true;
-  }
-  const int ctas = (a.batch + ksx1::kWarpsPerCta - 1) / ksx1::kWarpsPerCta;
-  const int sms = sm_count();
-  const cudaError_t ce = KS_LAUNCH_PDL(kern, (unsigned)(ctas < sms ? ctas : sms), (unsigned)(ksx1::kWarpsPerCta * 32), (size_t)smem, s, a);
-  if (ce != cudaSuccess) {
-    static char msg[160];
-    std::snprintf(msg, sizeof(msg), "warp32x1 kernel launch failed: %s", cudaGetErrorString(ce));
-    return fail(KS_ERR_LAUNCH, msg);
-  }
-  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32x1 kernel launch failed");
-}
-template <int CLS>
-int launch_adjstep(const KsEvalArgs& a, cudaStream_t s) {
-  return a.precond ? launch_warp32x1_pc<CLS, KS_OP_ADJSTEP, true>(a, s) : launch_warp32x1_pc<CLS, KS_OP_ADJSTEP, false>(a, s);
-}
-template <int CLS>
-int launch_adjmulti(const KsEvalArgs& a, cudaStream_t s) {
-  return a.precond ? launch_warp32x1_pc<CLS, KS_OP_ADJMULTI, true>(a, s) : launch_warp32x1_pc<CLS, KS_OP_ADJMULTI, false>(a, s);
-}
-template <int CLS, int OP>
-int launch_warp32(const KsEvalArgs& a, cudaStream_t s) {
-  if constexpr (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) {
-    if (g_warp32_variant == 4) {
-      if constexpr (OP == KS_OP_COSTGRAD) {
-        if (a.precond) return launch_warp32x1_pc<CLS, OP, true>(a, s);
-      }
-      return launch_warp32x1_pc<CLS, OP, false>(a, s);
-    }
-  }
-  return launch_warp32_as<CLS, OP>(a, s);
 }
 template <int CLS, int OP>
 int launch_generic(const ksg::GenArgs& ga, cudaStream_t s) {
@@ -148,12 +95,7 @@ int dispatch(int cls, int n, int m, const KsEvalArgs& a, void* ws, size_t ws_byt
   if constexpr (OP != ksg::KS_OP_TRANSFORM) {
     if (use_tile(n, m)) return launch_tile<OP>(cls, n, m, e, s);
     if (use_warp32(n, m)) {
-      switch (cls) {
-        case KS_ORBIT: return launch_warp32<KS_ORBIT, OP>(e, s);
-        case KS_RELATIVE: return launch_warp32<KS_RELATIVE, OP>(e, s);
-        case KS_SHIFT_REFLECTION: return launch_warp32<KS_SHIFT_REFLECTION, OP>(e, s);
-        default: return launch_warp32<KS_ANTISYMMETRIC, OP>(e, s);
-      }
+      return w32_run(cls, OP, e, s);
     }
   }
   ksg::GenArgs ga;
@@ -185,7 +127,7 @@ void ks_debug_tile(int enabled, int chunk_mb) {
   g_tile_mode = (enabled == 0 || enabled == 2) ? enabled : 1;
   if (chunk_mb > 0) g_tile_chunk_mb = chunk_mb;
 }
-void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant == 3 || variant == 4) ? variant : 4; }
+void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant >= 3 && variant <= 5) ? variant : 4; }
 
 int ks_mode_size(int cls, int n, int m) { return shape_ok(cls, n, m) ? (n - 1) * mode_cols(cls, m) : 0; }
 
@@ -436,7 +378,7 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
     return q;
   };
   if (check_every <= 0) check_every = 64;
-  if (use_warp32(n, m) && g_warp32_variant == 4) {
+  if (use_warp32(n, m) && g_warp32_variant >= 4) {
     // ---- fused path: ONE launch per pass (decide on the previous trial + evaluate the next one inside the x1 kernel)
     KsEvalArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -475,13 +417,7 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
       for (long done = 0; done < max_passes + A.inner; done += A.inner) {
         cudaMemsetAsync(A.n_live, 0, 4, s);
         A.first = (done == 0) ? 1 : 0;
-        int rc;
-        switch (cls) {
-          case KS_ORBIT: rc = launch_adjmulti<KS_ORBIT>(a, s); break;
-          case KS_RELATIVE: rc = launch_adjmulti<KS_RELATIVE>(a, s); break;
-          case KS_SHIFT_REFLECTION: rc = launch_adjmulti<KS_SHIFT_REFLECTION>(a, s); break;
-          default: rc = launch_adjmulti<KS_ANTISYMMETRIC>(a, s); break;
-        }
+        const int rc = w32_run(cls, KS_OP_ADJMULTI, a, s);
         if (rc != 0) return rc;
         passes += A.inner;
         int n_live = 0;
@@ -496,13 +432,7 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
     for (long it = 0; it < max_passes; ++it) {
       cudaMemsetAsync(A.n_live, 0, 4, s);
       A.first = (it == 0) ? 1 : 0;
-      int rc;
-      switch (cls) {
-        case KS_ORBIT: rc = launch_adjstep<KS_ORBIT>(a, s); break;
-        case KS_RELATIVE: rc = launch_adjstep<KS_RELATIVE>(a, s); break;
-        case KS_SHIFT_REFLECTION: rc = launch_adjstep<KS_SHIFT_REFLECTION>(a, s); break;
-        default: rc = launch_adjstep<KS_ANTISYMMETRIC>(a, s); break;
-      }
+      const int rc = w32_run(cls, KS_OP_ADJSTEP, a, s);
       if (rc != 0) return rc;
       ++passes;
       if ((it + 1) % check_every == 0 || it + 1 == max_passes) {
@@ -662,6 +592,9 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
     if (restart < 1) return fail(KS_ERR_ARG, "gmres restart must be >= 1");
     if (restart > N) restart = N;  // scipy: restart = min(restart, n)
   }
+  // _sparse_linalg_factory (optimize.py:1764, :1803-1850): gmres solves the normal equations unless the system is square,
+  // i.e. cdof().size == eqn().size, which for these classes means every parameter is constrained
+  const bool square = (method == 0 && n_free(cmask) == 0);
   const NkLayout lay = nk_layout(cls, n, m, batch, method, restart, cmask);
   if (!ws || ws_bytes < lay.total) return fail(KS_ERR_WORKSPACE, "workspace too small (see ks_newton_krylov_workspace_bytes)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -726,8 +659,12 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
     // right-hand side: -F  (and A^T(-F) for the normal equations)
     if ((rc = eval_eqn(modes, params, Fy, nullptr)) != 0) return rc;
     if (method == 0) {
-      KS_LAUNCH(kskry::negate_kernel, 296, 256, 0, s, Fy, Fy, (size_t)batch * nm);
-      if ((rc = op_rmatvec(Fy, rhs)) != 0) return rc;
+      if (square) {  // every parameter constrained: GMRES on J dx = -F itself                     (:1803-1850)
+        KS_LAUNCH(kskry::negate_kernel, 296, 256, 0, s, Fy, rhs, (size_t)batch * nm);
+      } else {       // normal equations A^T A dx = A^T (-F)                                        (:1764-1797)
+        KS_LAUNCH(kskry::negate_kernel, 296, 256, 0, s, Fy, Fy, (size_t)batch * nm);
+        if ((rc = op_rmatvec(Fy, rhs)) != 0) return rc;
+      }
       kskry::GmresState g;
       g.V = reinterpret_cast<double*>(at(15)); g.H = reinterpret_cast<double*>(at(16));
       g.G = reinterpret_cast<double*>(at(17)); g.S = reinterpret_cast<double*>(at(18));
@@ -754,8 +691,12 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
           if (!poll(0, active)) return fail(KS_ERR_LAUNCH, "newton-krylov: device error while polling");
           if (active == 0) break;
         }
-        if ((rc = op_matvec(vin, Fy)) != 0) return rc;
-        if ((rc = op_rmatvec(Fy, wout)) != 0) return rc;
+        if (square) {
+          if ((rc = op_matvec(vin, wout)) != 0) return rc;
+        } else {
+          if ((rc = op_matvec(vin, Fy)) != 0) return rc;
+          if ((rc = op_rmatvec(Fy, wout)) != 0) return rc;
+        }
         cudaMemsetAsync(counters, 0, 4, s);
         if (gm_cluster > 0) {
           cudaError_t ce;

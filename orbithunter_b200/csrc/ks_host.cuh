@@ -13,20 +13,45 @@ inline int fail(int code, const char* msg) {
   std::snprintf(g_err, sizeof(g_err), "%s", msg);
   return code;
 }
+// Per-device caches.  cudaFuncSetAttribute and the SM count belong to the CURRENT device, and one process may drive
+// several GPUs (BatchedOrbitKS switches devices per call), so both are keyed by cudaGetDevice().
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+#ifdef KS_HOST_EMUL
+  return 0;
+#else
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+#endif
+}
 inline int sm_count() {
 #ifdef KS_HOST_EMUL
   return ks_emul::device_sm_count;
 #else
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-    cached = n;
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
   }
-  return cached;
+  return cached[dev];
 #endif
 }
+// Opt a kernel into `bytes` of dynamic shared memory once per device.  One DynSmemOptIn object per kernel
+// instantiation (a function-local static at the launch site).
+struct DynSmemOptIn {
+  bool done[kMaxDevices] = {};
+  template <class K>
+  bool ensure(K kernel, int bytes) {
+    const int dev = current_device();
+    if (done[dev]) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 inline int mode_cols(int cls, int m) { return (cls == KS_ORBIT || cls == KS_RELATIVE) ? m - 2 : m / 2 - 1; }
 inline int ilog2_exact(int v) {
   int l = 0;
@@ -56,3 +81,9 @@ int ks_tile_run_c0(int op, int n, int m, int chunk, const KsEvalArgs& a, cudaStr
 int ks_tile_run_c1(int op, int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s);
 int ks_tile_run_c2(int op, int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s);
 int ks_tile_run_c3(int op, int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s);
+// 32x32 register-resident kernels, one translation unit per symmetry class (ks_w32_c{0..3}.cu); `variant` selects the
+// kernel build for eqn / costgrad (3, 4, 5: see ks_debug_warp32_variant)
+int ks_w32_run_c0(int op, int variant, const KsEvalArgs& a, cudaStream_t s);
+int ks_w32_run_c1(int op, int variant, const KsEvalArgs& a, cudaStream_t s);
+int ks_w32_run_c2(int op, int variant, const KsEvalArgs& a, cudaStream_t s);
+int ks_w32_run_c3(int op, int variant, const KsEvalArgs& a, cudaStream_t s);

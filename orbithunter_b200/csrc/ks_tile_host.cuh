@@ -85,12 +85,8 @@ int tile_chunk_run(kst::TileArgs& ta, cudaStream_t s) {
 template <int CLS, int OP>
 int launch_fused64(const KsEvalArgs& a, cudaStream_t s) {
   auto kern = kst::tile_fused64_kernel<CLS, OP>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kst::F64::smem_bytes) != cudaSuccess)
-      return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(fused64) failed");
-    attr_done = true;
-  }
+  static DynSmemOptIn optin;
+  if (!optin.ensure(kern, (int)kst::F64::smem_bytes)) return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(fused64) failed");
   kst::TileArgs ta;
   std::memset(&ta, 0, sizeof(ta));
   ta.e = a;

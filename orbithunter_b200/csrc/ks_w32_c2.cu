@@ -1,0 +1,3 @@
+// 32x32 register-resident kernels, symmetry class 2 (see ks_w32_host.cuh)
+#define KS_W32_CLS 2
+#include "ks_w32_host.cuh"

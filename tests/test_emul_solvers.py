@@ -86,3 +86,21 @@ def test_newton_krylov_matches_scipy_based_oracle(cid, method, precond, gm_clust
         assert abs(cost[b] - st["cost"]) <= tol * max(1.0, st["cost"])
         assert relerr(Mo[b], rm) < tol * 10
     assert cnt[3] == 2 and cnt[0] > 0
+
+
+@pytest.mark.parametrize("cid,precond", [(0, False), (2, True), (1, False)])
+def test_gmres_square_system_when_every_parameter_is_constrained(cid, precond):
+    """cdof().size == eqn().size (t, x and s all constrained, continuation's case): the reference hands GMRES the square
+    system J dx = -F itself, not the normal equations (optimize.py:1764, :1803-1850)."""
+    n = m = 16
+    B = 2
+    M = np.stack([ko.populate_state(44.0, 44.0, n, m, 3 + s, cid) for s in range(B)])
+    p = np.tile([44.0, 44.0, 0.3 if cid == 1 else 0.0], (B, 1))
+    cons = (True, True, True)
+    Mo, po, status, nit, cost, cnt = E.newton_krylov(cid, n, m, M, p, 7, 0, maxiter=2, precond=precond, restart=10, inner=2, rtol=1e-5)
+    for b in range(B):
+        rm, rp, st = ko.newton_krylov(M[b], p[b], cid, constraints=cons, method="gmres", maxiter=2, preconditioning=precond,
+                                      scipy_kwargs=dict(restart=10, maxiter=2))
+        assert (int(status[b]), int(nit[b])) == (st["status"], st["nit"])
+        assert abs(cost[b] - st["cost"]) <= 1e-10 * max(1.0, st["cost"])
+        assert relerr(Mo[b], rm) < 1e-9 and np.array_equal(po[b], p[b])

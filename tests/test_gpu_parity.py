@@ -157,6 +157,35 @@ def test_warp32_matches_generic_kernel(cid):
     assert relerr(g1.cpu_state(), g2.cpu_state()) < TOL and np.allclose(c1.cpu().numpy(), c2.cpu().numpy(), rtol=1e-13)
 
 
+@pytest.mark.parametrize("variant", [3, 4, 5])
+@pytest.mark.parametrize("cid", range(4))
+def test_warp32_variants_vs_oracle(cid, variant):
+    """Every build of the 32x32 eqn / costgrad kernel (two orbits per warp; one orbit per warp with 8 and with 12 warps per
+    SM) against the oracle, on a batch that spans several rounds of the persistent warps and with mixed constraints."""
+    from orbithunter_b200 import _lib
+
+    B = 3 * 148 * 12 + 77
+    M = np.stack([ko.populate_state(44.0, 33.4, 32, 32, s % 97, cid) for s in range(B)]) * (1.0 + 1e-3 * np.arange(B)[:, None, None])
+    rng = np.random.RandomState(cid)
+    p = np.stack([44.0 + rng.rand(B), 33.4 + rng.rand(B), (rng.randn(B) if cid == 1 else np.zeros(B))], axis=1)
+    L = _lib.lib()
+    L.ks_debug_warp32_variant(variant)
+    try:
+        for cons in (ko.default_constraints(cid), (True, False, False)):
+            u = _b(cid, M, p, cons)
+            F, c = u.eqn(return_cost=True)
+            assert relerr(F.cpu_state(), ko.eqn(M, p, cid)) < TOL
+            assert np.allclose(c.cpu().numpy(), ko.cost(M, p, cid), rtol=1e-12)
+            for pc in (False, True):
+                c2, gr, Fo = u.costgrad(preconditioning=pc, return_eqn=True)
+                oc, ogs, ogp, oF = ko.costgrad(M, p, cid, cons, pc)
+                assert relerr(gr.cpu_state(), ogs) < TOL and relerr(Fo.cpu_state(), oF) < TOL
+                assert np.allclose(c2.cpu().numpy(), oc, rtol=1e-12)
+                assert np.allclose(gr.cpu_parameters(), ogp, rtol=1e-10, atol=1e-10 * np.max(np.abs(ogp)) + 1e-300)
+    finally:
+        L.ks_debug_warp32_variant(4)
+
+
 @pytest.mark.parametrize("cid", range(4))
 @pytest.mark.parametrize("shape,B", [((64, 64), 97), ((128, 64), 9), ((64, 256), 5), ((256, 256), 3)])
 def test_tile_matches_generic_kernel(cid, shape, B):
