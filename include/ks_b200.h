@@ -37,8 +37,14 @@ const char* ks_last_error(void);
 /* test hook: route 32x32 through the generic-size kernel instead of the register-resident one (cross-check). */
 void ks_debug_force_generic(int on);
 /* tuning hook, 32x32 kernel build variant: 3 = two orbits per warp, 7 warps/SM, global reads staged with cp.async
- * (all ops); 4 (default) = one orbit per warp, 8 warps/SM, all state in registers (eqn and costgrad; other ops use 3). */
+ * (all ops); 4 (default) = one orbit per warp, 8 warps/SM, all state in registers (eqn and costgrad; other ops use 3);
+ * 5 = one orbit per warp, 12 warps/SM, field rows stashed in shared memory (eqn and costgrad);
+ * 6 = variant 4's work split with the two warps of each scheduler taking turns on the fp64 pipe (eqn and costgrad). */
 void ks_debug_warp32_variant(int variant);
+/* tuning hook, 32x32 kernels: nanoseconds between the start of the warps that share one SM scheduler (default 0). */
+void ks_debug_warp32_stagger(int ns);
+/* tuning hook, 32x32 variant 6: 1 (default) = token passing between the two warp groups, 0 = free-running warps. */
+void ks_debug_warp32_pingpong(int on);
 /* tuning hook, large-grid (n, m in {64, 128, 256}) tile path: enabled = 0 routes those shapes through the generic
  * kernel (cross-check), 1 (default) = tile path with the CTA-resident fused kernel at 64x64, 2 = multi-pass tiles for
  * every shape; chunk_mb > 0 sets the workspace budget that bounds how many orbits one pass sequence covers. */
@@ -109,11 +115,14 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
                        int32_t* status_out, int32_t* nit_out, double* cost_out, double* step_out, int check_every,
                        int* passes_out, void* ws, size_t ws_bytes, void* stream);
 
-/* hunt(..., 'gmres' | 'lsqr'): _scipy_sparse_linalg_solver_wrapper (optimize.py:1196-1404) for a whole batch.
+/* hunt(..., 'gmres' | 'lsqr' | 'lsmr'): _scipy_sparse_linalg_solver_wrapper (optimize.py:1196-1404) for a whole batch.
  * method 0 = GMRES on the normal equations A^T A dx = -A^T F (optimize.py:1760-1797; restart / inner_maxiter = restart
  * cycles / rtol / atol as scipy.sparse.linalg.gmres; preconditioning = OrbitKS.preconditioner as M);
  * method 1 = LSQR on the rectangular system J dx = -F (optimize.py:1731-1759; inner_maxiter = iter_lim, atol, btol,
- * conlim as scipy.sparse.linalg.lsqr, damp = 0).  Each outer step takes the full step first and halves while
+ * conlim as scipy.sparse.linalg.lsqr, damp = 0); method 2 = LSMR on the same system (optimize.py:1319-1321;
+ * inner_maxiter = maxiter, atol, btol, conlim as scipy.sparse.linalg.lsmr, damp = 0); when every parameter is
+ * constrained (cdof == Nm) method 0 solves the square system J dx = -F itself, as the reference does (optimize.py:1803-1850).
+ * Each outer step takes the full step first and halves while
  * next_cost > cost and step > min_step, then _process_correction.  modes/params updated in place; status/nit/cost per
  * orbit as for ks_adjoint_descent.  Synchronises the stream while polling.  counters_out (host, 4 x int64, may be
  * NULL): operator applications, solver steps, line-search evaluations, outer iterations. */

@@ -456,8 +456,8 @@ def normal_operator(modes, params, cls, constraints):
 
 def newton_krylov(modes, params, cls=ORBIT, constraints=None, method="gmres", tol=1e-6, ftol=1e-9, maxiter=10000,
                   min_step=1e-6, preconditioning=False, scipy_kwargs=None):
-    """optimize.py:1196-1404 for ONE orbit with method in {gmres, lsqr}; inner solver is SciPy's, as in the reference."""
-    from scipy.sparse.linalg import LinearOperator, gmres, lsqr
+    """optimize.py:1196-1404 for ONE orbit with method in {gmres, lsqr, lsmr}; inner solver is SciPy's, as in the reference."""
+    from scipy.sparse.linalg import LinearOperator, gmres, lsmr, lsqr
 
     constraints = default_constraints(cls) if constraints is None else constraints
     scipy_kwargs = dict(scipy_kwargs or {})
@@ -470,7 +470,7 @@ def newton_krylov(modes, params, cls=ORBIT, constraints=None, method="gmres", to
     while c > tol and stats["status"] == -1:
         step = 1.0
         N = cdof(modes, params, constraints).size
-        if method == "lsqr":
+        if method in ("lsqr", "lsmr"):
             def mv(v):
                 vs, vp = from_cdof(np.asarray(v).ravel(), shape, constraints)
                 return matvec(modes, params, vs, vp, cls, constraints).ravel()
@@ -481,7 +481,7 @@ def newton_krylov(modes, params, cls=ORBIT, constraints=None, method="gmres", to
 
             A = LinearOperator((modes.size, N), matvec=mv, rmatvec=rmv, dtype=float)
             b = -1.0 * eqn(modes, params, cls).ravel()
-            x = lsqr(A, b, **scipy_kwargs)[0]
+            x = (lsqr if method == "lsqr" else lsmr)(A, b, **scipy_kwargs)[0]
         else:
             if N == modes.size:
                 # square system (every parameter constrained): J dx = -F itself, optimize.py:1803-1850

@@ -89,6 +89,32 @@ def gen_lsmr(out):
             print(key, r.status, r.nit, r.costs, flush=True)
 
 
+def gen_deriv(out):
+    """dt / dx (orders 1-4; SR / Anti odd orders go through spatial_modes), precondition and the preconditioner diagonal of
+    the unmodified reference (ks/orbits.py:379-524, :3190-3227, :3583-3619, :1034-1141) on a 32x32 and a 16x24 seed."""
+    for cid, C in CLASSES.items():
+        for (n, m) in ((32, 32), (16, 24)):
+            o = C(parameters=(44.0, 33.4, 1.3 if cid == 1 else 0.0)).populate(attr="state", seed=11 + cid, discretization=(n, m))
+            o = C(**{**vars(o), "parameters": (44.0, 33.4, 1.3 if cid == 1 else 0.0)})
+            key = f"deriv/{cid}_{n}x{m}"
+            out[key + "/modes"] = o.state
+            out[key + "/params"] = np.array(o.parameters, dtype=float)
+            for order in (1, 2, 3, 4):
+                out[key + f"/dt{order}"] = o.dt(order=order).state
+                out[key + f"/dx{order}"] = o.dx(order=order).state
+                out[key + f"/dx{order}_field"] = o.dx(order=order, return_basis="field").state
+            out[key + "/dt1_field"] = o.dt(return_basis="field").state
+            g = o.rmatvec(o)
+            pc = g.precondition(pmult=o.preconditioning_parameters())
+            out[key + "/rmatvec_self"] = g.state
+            out[key + "/rmatvec_self_params"] = np.array(g.parameters, dtype=float)
+            out[key + "/precond"] = pc.state
+            out[key + "/precond_params"] = np.array(pc.parameters, dtype=float)
+            P = o.preconditioner()
+            out[key + "/preconditioner_diag"] = np.asarray(P.matvec(np.ones(P.shape[0]))).ravel()
+    print("deriv ok", flush=True)
+
+
 def _cfg0_one(seed):
     import warnings as w
 
@@ -121,7 +147,7 @@ def gen_cfg0(procs):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg2,cfg3,square,lsq")
+    ap.add_argument("--only", default="cfg2,cfg3,square,lsq,deriv")
     ap.add_argument("--procs", type=int, default=os.cpu_count())
     args = ap.parse_args()
     which = set(args.only.split(","))
@@ -135,7 +161,9 @@ def main():
         gen_square(out)
     if "lsq" in which:
         gen_lsmr(out)
-    if which & {"cfg2", "cfg3", "square", "lsq"}:
+    if "deriv" in which:
+        gen_deriv(out)
+    if which & {"cfg2", "cfg3", "square", "lsq", "deriv"}:
         np.savez_compressed(path, **out)
         print(path, os.path.getsize(path))
     if "cfg0" in which:

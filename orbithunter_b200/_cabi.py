@@ -7,6 +7,8 @@ _SIG = {
     "ks_last_error": (C.c_char_p, []),
     "ks_debug_force_generic": (None, [C.c_int]),
     "ks_debug_warp32_variant": (None, [C.c_int]),
+    "ks_debug_warp32_stagger": (None, [C.c_int]),
+    "ks_debug_warp32_pingpong": (None, [C.c_int]),
     "ks_debug_tile": (None, [C.c_int, C.c_int]),
     "ks_debug_gmres_cluster": (None, [C.c_int]),
     "ks_debug_adjoint_inner": (None, [C.c_int]),

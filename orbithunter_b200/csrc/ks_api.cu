@@ -18,6 +18,8 @@ namespace {
 bool shape_ok(int cls, int n, int m) {
   return cls >= 0 && cls <= 3 && n >= 4 && m >= 4 && (n % 2 == 0) && (m % 2 == 0) && n <= 4096 && m <= 4096;
 }
+int g_w32_pingpong = 0;
+int g_w32_stagger_ns = 0;  // tuning: start delay between the warps of one scheduler in the 32x32 kernels
 bool g_force_generic = false;  // debug/test switch: route 32x32 through the generic kernel as a cross-check
 int g_warp32_variant = 4;  // 32x32 eqn / costgrad / adjoint descent: 4 = one orbit per warp (ks_warp32x1.cuh, default), 3 = two orbits per
                            // warp (ks_warp32.cuh, which always serves matvec / rmatvec)
@@ -33,7 +35,10 @@ int generic_grid(int batch) {
   return batch < cap ? batch : cap;
 }
 // 32x32 kernels: instantiated per symmetry class in ks_w32_c{0..3}.cu (see ks_w32_host.cuh)
-int w32_run(int cls, int op, const KsEvalArgs& a, cudaStream_t s) {
+int w32_run(int cls, int op, const KsEvalArgs& a0, cudaStream_t s) {
+  KsEvalArgs a = a0;
+  a.stagger_ns = g_w32_stagger_ns;
+  a.pingpong = g_w32_pingpong;
   switch (cls) {
     case KS_ORBIT: return ks_w32_run_c0(op, g_warp32_variant, a, s);
     case KS_RELATIVE: return ks_w32_run_c1(op, g_warp32_variant, a, s);
@@ -127,7 +132,9 @@ void ks_debug_tile(int enabled, int chunk_mb) {
   g_tile_mode = (enabled == 0 || enabled == 2) ? enabled : 1;
   if (chunk_mb > 0) g_tile_chunk_mb = chunk_mb;
 }
-void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant >= 3 && variant <= 5) ? variant : 4; }
+void ks_debug_warp32_pingpong(int mode) { g_w32_pingpong = mode; }
+void ks_debug_warp32_stagger(int ns) { g_w32_stagger_ns = ns < 0 ? 0 : ns; }
+void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant >= 3 && variant <= 6) ? variant : 4; }
 
 int ks_mode_size(int cls, int n, int m) { return shape_ok(cls, n, m) ? (n - 1) * mode_cols(cls, m) : 0; }
 
@@ -553,7 +560,7 @@ NkLayout nk_layout(int cls, int n, int m, int batch, int method, int restart, ui
   take((size_t)batch * 4);                                    // 10 live
   take((size_t)batch * 4);                                    // 11 searching
   take(256);                                                  // 12 counters
-  take((size_t)batch * 16 * 8);                               // 13 solver scalars
+  take((size_t)batch * 32 * 8);                               // 13 solver scalars (GMRES SC_COUNT = 8, LSQR / LSMR LQ_COUNT = 32)
   take((size_t)batch * 8 * 4);                                // 14 solver ints
   if (method == 0) {
     take((size_t)batch * (restart + 1) * N * 8);              // 15 V
@@ -564,7 +571,7 @@ NkLayout nk_layout(int cls, int n, int m, int batch, int method, int restart, ui
     take(batch * nm * 8);                                     // 15 u
     take(batch * N * 8);                                      // 16 v
     take(batch * N * 8);                                      // 17 w vector
-    take(8);                                                  // 18 unused
+    take(batch * N * 8);                                      // 18 hbar (LSMR)
   }
   L.total = p;
   return L;
@@ -572,7 +579,7 @@ NkLayout nk_layout(int cls, int n, int m, int batch, int method, int restart, ui
 }  // namespace
 
 size_t ks_newton_krylov_workspace_bytes(int cls, int n, int m, int batch, int method, int restart) {
-  if (!shape_ok(cls, n, m) || batch <= 0 || method < 0 || method > 1 || (method == 0 && restart < 1)) return 0;
+  if (!shape_ok(cls, n, m) || batch <= 0 || method < 0 || method > 2 || (method == 0 && restart < 1)) return 0;
   return nk_layout(cls, n, m, batch, method, restart, 0).total;
 }
 
@@ -582,7 +589,7 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
                      int32_t* nit_out, double* cost_out, long long* counters_out, int check_every, void* ws,
                      size_t ws_bytes, void* stream) {
   if (!shape_ok(cls, n, m)) return fail(KS_ERR_SHAPE, "unsupported class / discretization (need even n, m >= 4)");
-  if (batch < 0 || maxiter < 0 || method < 0 || method > 1) return fail(KS_ERR_ARG, "bad batch / maxiter / method");
+  if (batch < 0 || maxiter < 0 || method < 0 || method > 2) return fail(KS_ERR_ARG, "bad batch / maxiter / method");
   if (counters_out) counters_out[0] = counters_out[1] = counters_out[2] = counters_out[3] = 0;
   if (batch == 0) return 0;
   if (!modes || !params || !status_out || !nit_out || !cost_out) return fail(KS_ERR_ARG, "null array argument");
@@ -719,7 +726,8 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
       KS_LAUNCH(kskry::negate_kernel, 296, 256, 0, s, Fy, rhs, (size_t)batch * nm);
       kskry::LsqrState g;
       g.u = reinterpret_cast<double*>(at(15)); g.v = reinterpret_cast<double*>(at(16));
-      g.wv = reinterpret_cast<double*>(at(17)); g.x = xsol; g.b = rhs; g.vin = vin; g.w = wout;
+      g.wv = reinterpret_cast<double*>(at(17)); g.hbar = reinterpret_cast<double*>(at(18)); g.lsmr = (method == 2) ? 1 : 0;
+      g.x = xsol; g.b = rhs; g.vin = vin; g.w = wout;
       g.sc = reinterpret_cast<double*>(at(13)); g.ic = reinterpret_cast<int*>(at(14));
       g.live = live; g.n_active = counters;
       g.B = batch; g.M = nm; g.N = N; g.ld = N; g.iter_lim = inner_maxiter; g.atol = atol; g.btol = btol; g.conlim = conlim;

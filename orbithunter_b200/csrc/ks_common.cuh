@@ -52,6 +52,8 @@ struct KsEvalArgs {
   int v_ld, out_ld;
   int v_tail;             // matvec: read (dT, dL, dS) from vmodes[b*v_ld + Nm + slot] instead of vparams
   int out_tail;           // rmatvec/costgrad: write free parameter components to out_state[b*out_ld + Nm + slot]
+  int pingpong;           // 32x32 variant 6: the two warp groups of a CTA take turns on the fp64 pipe (ks_debug_warp32_pingpong)
+  int stagger_ns;         // 32x32 kernels: start delay between the warps of one scheduler (tuning, ks_debug_warp32_stagger)
   KsAdjFused adj;         // KS_OP_ADJSTEP / KS_OP_ADJMULTI only
 };
 

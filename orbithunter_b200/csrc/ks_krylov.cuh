@@ -570,13 +570,16 @@ __global__ void __launch_bounds__(kThreads) gmres_step_cluster_kernel(const Gmre
 // LSQR (SciPy _isolve/lsqr.py, damp = 0, x0 = None).  Phases: 0 = waiting for A v, 1 = waiting for A^T u.
 // ---------------------------------------------------------------------------------------------------------------
 enum { LQ_ALFA = 0, LQ_BETA, LQ_RHOBAR, LQ_PHIBAR, LQ_ANORM, LQ_DDNORM, LQ_XXNORM, LQ_Z, LQ_CS2, LQ_SN2, LQ_BNORM, LQ_RES2,
-       LQ_COUNT = 16 };
+       // LSMR only (SciPy _isolve/lsmr.py): the names of its scalar recurrences
+       LM_ZETABAR, LM_ALPHABAR, LM_RHO, LM_CBAR, LM_SBAR, LM_BETADD, LM_BETAD, LM_RHODOLD, LM_TAUTILDEOLD, LM_THETATILDE, LM_ZETA,
+       LM_D, LM_NORMA2, LM_MAXRBAR, LM_MINRBAR, LQ_COUNT = 32 };
 enum { LI_PHASE = 0, LI_ITN, LI_ISTOP, LI_DONE, LI_COUNT = 8 };
 
 struct LsqrState {
   double* u;        // [B][M]   left vectors (length Nm)
   double* v;        // [B][N]   right vectors (cdof)
-  double* wv;       // [B][N]
+  double* wv;       // [B][N]   LSQR: w; LSMR: h
+  double* hbar;     // [B][N]   LSMR only
   double* x;        // [B][N]
   const double* b;  // [B][M]   right-hand side (-F)
   double* vin;      // [B][max(M,N)]  next operator input
@@ -586,6 +589,7 @@ struct LsqrState {
   const int* live;
   int* n_active;
   int B, M, N, ld, iter_lim;
+  int lsmr;         // 0: LSQR recurrences, 1: LSMR recurrences on the same Golub-Kahan bidiagonalisation
   double atol, btol, conlim;
 };
 
@@ -688,7 +692,7 @@ __global__ void __launch_bounds__(kThreads) lsqr_step_kernel(const LsqrState g) 
     }
     if (threadIdx.x == 0) {
       sc[LQ_BETA] = beta;
-      if (beta > 0.0) {
+      if (beta > 0.0 && !g.lsmr) {
         const double an = sc[LQ_ANORM];
         sc[LQ_ANORM] = sqrt(an * an + alfa * alfa + beta * beta);
       }
@@ -715,21 +719,114 @@ __global__ void __launch_bounds__(kThreads) lsqr_step_kernel(const LsqrState g) 
     }
   }
   if (itn == 0) {
-    // set-up: w = v, rhobar = alfa, phibar = beta; arnorm = alfa*beta == 0 -> finished with x = 0
+    // set-up: w = v (LSMR: h = v, hbar = 0), rhobar = alfa, phibar = beta; arnorm = alfa*beta == 0 -> finished with x = 0
     for (int i = threadIdx.x; i < g.N; i += kThreads) {
       wv[i] = v[i];
       vin[i] = v[i];
+      if (g.lsmr) g.hbar[(size_t)b * g.N + i] = 0.0;
     }
     if (threadIdx.x == 0) {
       sc[LQ_ALFA] = alfa;
       sc[LQ_RHOBAR] = alfa;
       sc[LQ_PHIBAR] = beta;
+      if (g.lsmr) {  // lsmr.py "Initialize variables for 1st iteration / for estimation of ||r|| / of ||A|| and cond(A)"
+        sc[LM_ZETABAR] = alfa * beta; sc[LM_ALPHABAR] = alfa; sc[LM_RHO] = 1.0; sc[LQ_RHOBAR] = 1.0; sc[LM_CBAR] = 1.0;
+        sc[LM_SBAR] = 0.0; sc[LM_BETADD] = beta; sc[LM_BETAD] = 0.0; sc[LM_RHODOLD] = 1.0; sc[LM_TAUTILDEOLD] = 0.0;
+        sc[LM_THETATILDE] = 0.0; sc[LM_ZETA] = 0.0; sc[LM_D] = 0.0; sc[LM_NORMA2] = alfa * alfa; sc[LM_MAXRBAR] = 0.0;
+        sc[LM_MINRBAR] = 1e100;
+      }
       ic[LI_PHASE] = 0;
       if (alfa * beta == 0.0 || g.iter_lim <= 0) {
         ic[LI_DONE] = 1;
       } else {
         atomicAdd(g.n_active, 1);
       }
+    }
+    return;
+  }
+  if (g.lsmr) {
+    // ---- LSMR (lsmr.py main loop after the bidiagonalisation step; damp = 0, so Qhat is the identity: chat = 1, shat = 0) ----
+    if (threadIdx.x == 0) {
+      const double alphabar0 = sc[LM_ALPHABAR];
+      double chat, shat, alphahat;
+      sym_ortho(alphabar0, 0.0, chat, shat, alphahat);
+      const double rhoold = sc[LM_RHO];
+      double c_, s_, rho;
+      sym_ortho(alphahat, beta, c_, s_, rho);
+      const double thetanew = s_ * alfa;
+      sc[LM_ALPHABAR] = c_ * alfa;
+      const double rhobarold = sc[LQ_RHOBAR], zetaold = sc[LM_ZETA];
+      const double thetabar = sc[LM_SBAR] * rho, rhotemp = sc[LM_CBAR] * rho;
+      double cbar, sbar, rhobar;
+      sym_ortho(sc[LM_CBAR] * rho, thetanew, cbar, sbar, rhobar);
+      const double zeta = cbar * sc[LM_ZETABAR];
+      sc[LM_ZETABAR] = -sbar * sc[LM_ZETABAR];
+      sc[LM_RHO] = rho; sc[LQ_RHOBAR] = rhobar; sc[LM_CBAR] = cbar; sc[LM_SBAR] = sbar; sc[LM_ZETA] = zeta;
+      shd[0] = -(thetabar * rho / (rhoold * rhobarold));  // hbar scale
+      shd[1] = zeta / (rho * rhobar);                      // x step along hbar
+      shd[2] = -(thetanew / rho);                          // h scale
+      // estimate of |r|
+      const double betaacute = chat * sc[LM_BETADD], betacheck = -shat * sc[LM_BETADD];
+      const double betahat = c_ * betaacute;
+      sc[LM_BETADD] = -s_ * betaacute;
+      const double thetatildeold = sc[LM_THETATILDE];
+      double ctildeold, stildeold, rhotildeold;
+      sym_ortho(sc[LM_RHODOLD], thetabar, ctildeold, stildeold, rhotildeold);
+      sc[LM_THETATILDE] = stildeold * rhobar;
+      sc[LM_RHODOLD] = ctildeold * rhobar;
+      sc[LM_BETAD] = -stildeold * sc[LM_BETAD] + ctildeold * betahat;
+      sc[LM_TAUTILDEOLD] = (zetaold - thetatildeold * sc[LM_TAUTILDEOLD]) / rhotildeold;
+      const double taud = (zeta - sc[LM_THETATILDE] * sc[LM_TAUTILDEOLD]) / sc[LM_RHODOLD];
+      sc[LM_D] += betacheck * betacheck;
+      const double dd = sc[LM_BETAD] - taud;
+      shd[3] = sqrt(sc[LM_D] + dd * dd + sc[LM_BETADD] * sc[LM_BETADD]);  // normr
+      // estimates of |A| and cond(A)
+      double na2 = sc[LM_NORMA2] + beta * beta;
+      shd[4] = sqrt(na2);                                                   // normA
+      sc[LM_NORMA2] = na2 + alfa * alfa;
+      sc[LM_MAXRBAR] = fmax(sc[LM_MAXRBAR], rhobarold);
+      if (itn > 1) sc[LM_MINRBAR] = fmin(sc[LM_MINRBAR], rhobarold);
+      shd[5] = fmax(sc[LM_MAXRBAR], rhotemp) / fmin(sc[LM_MINRBAR], rhotemp);  // condA
+      sc[LQ_ALFA] = alfa;
+    }
+    __syncthreads();
+    const double sh_hbar = shd[0], sx = shd[1], sh_h = shd[2];
+    double* hb = g.hbar + (size_t)b * g.N;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < g.N; i += kThreads) {
+      const double hbn = fma(sh_hbar, hb[i], wv[i]);  // hbar = h + scale * hbar   (hbar *= scale; hbar += h)
+      hb[i] = hbn;
+      const double xn = x[i] + sx * hbn;
+      x[i] = xn;
+      acc += xn * xn;
+      wv[i] = fma(sh_h, wv[i], v[i]);                  // h = v + scale * h
+      vin[i] = v[i];
+    }
+    const double normx = sqrt(block_sum(acc, sh));
+    if (threadIdx.x == 0) {
+      const double normr = shd[3], normA = shd[4], condA = shd[5], normb = sc[LQ_BNORM];
+      const double zb = sc[LM_ZETABAR];
+      const double normar = zb < 0 ? -zb : zb;
+      const double ctol = g.conlim > 0 ? 1.0 / g.conlim : 0.0;
+      const double test1 = normr / normb;
+      const double test2 = (normA * normr) != 0.0 ? normar / (normA * normr) : INFINITY;
+      const double test3 = 1.0 / condA;
+      const double t1 = test1 / (1.0 + normA * normx / normb);
+      const double rtol = g.btol + g.atol * normA * normx / normb;
+      int istop = 0;
+      if (itn >= g.iter_lim) istop = 7;
+      if (1.0 + test3 <= 1.0) istop = 6;
+      if (1.0 + test2 <= 1.0) istop = 5;
+      if (1.0 + t1 <= 1.0) istop = 4;
+      if (test3 <= ctol) istop = 3;
+      if (test2 <= g.atol) istop = 2;
+      if (test1 <= rtol) istop = 1;
+      ic[LI_ISTOP] = istop;
+      ic[LI_PHASE] = 0;
+      if (istop != 0)
+        ic[LI_DONE] = 1;
+      else
+        atomicAdd(g.n_active, 1);
     }
     return;
   }

@@ -46,6 +46,7 @@ inline cudaError_t ks_launch_cluster(void (*kernel)(KArgs...), unsigned grid, un
 // programmatic dependent launch (sm_90+): the launch processing and CTA scheduling of a kernel overlap the tail of the
 // previous kernel in the stream; the kernel itself waits (ks_pdl_wait) before it touches global memory, so stream order
 // is preserved.
+__device__ __forceinline__ void ks_nanosleep(unsigned ns) { asm volatile("nanosleep.u32 %0;" ::"r"(ns)); }
 __device__ __forceinline__ void ks_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void ks_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <class... KArgs, class... Args>

@@ -7,6 +7,7 @@
 #include "ks_warp32.cuh"
 #include "ks_warp32x1.cuh"
 #include "ks_warp32x3.cuh"
+#include "ks_warp32pp.cuh"
 
 #ifndef KS_W32_CLS
 #error "define KS_W32_CLS (0..3) before including ks_w32_host.cuh"
@@ -72,6 +73,23 @@ int launch_warp32x3_pc(const KsEvalArgs& a, cudaStream_t s) {
   }
   return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32x3 kernel launch failed");
 }
+// variant 6: variant 4's work split, the two warp groups of a CTA take turns on the fp64 pipe (ks_warp32pp.cuh)
+template <int CLS, int OP, bool PC>
+int launch_warp32pp_pc(const KsEvalArgs& a, cudaStream_t s) {
+  auto kern = kspp::ks_warp32pp_kernel<CLS, OP, PC>;
+  static DynSmemOptIn optin;
+  if (!optin.ensure(kern, kspp::kSmemBytes)) return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(warp32pp) failed");
+  const int ctas = (a.batch + kspp::kWarpsPerCta - 1) / kspp::kWarpsPerCta;
+  const int sms = sm_count();
+  const cudaError_t ce = KS_LAUNCH_PDL(kern, (unsigned)(ctas < sms ? ctas : sms), (unsigned)(kspp::kWarpsPerCta * 32),
+                                       (size_t)kspp::kSmemBytes, s, a);
+  if (ce != cudaSuccess) {
+    static char msg[160];
+    std::snprintf(msg, sizeof(msg), "warp32pp kernel launch failed: %s", cudaGetErrorString(ce));
+    return fail(KS_ERR_LAUNCH, msg);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "warp32pp kernel launch failed");
+}
 template <int CLS>
 int launch_adjstep(const KsEvalArgs& a, cudaStream_t s) {
   return a.precond ? launch_warp32x1_pc<CLS, KS_OP_ADJSTEP, true>(a, s) : launch_warp32x1_pc<CLS, KS_OP_ADJSTEP, false>(a, s);
@@ -83,6 +101,12 @@ int launch_adjmulti(const KsEvalArgs& a, cudaStream_t s) {
 template <int CLS, int OP>
 int launch_warp32(int variant, const KsEvalArgs& a, cudaStream_t s) {
   if constexpr (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) {
+    if (variant == 6) {
+      if constexpr (OP == KS_OP_COSTGRAD) {
+        if (a.precond) return launch_warp32pp_pc<CLS, OP, true>(a, s);
+      }
+      return launch_warp32pp_pc<CLS, OP, false>(a, s);
+    }
     if (variant == 5) {
       if constexpr (OP == KS_OP_COSTGRAD) {
         if (a.precond) return launch_warp32x3_pc<CLS, OP, true>(a, s);

@@ -1,42 +1,59 @@
-// 32x32 eqn / costgrad, "one orbit per warp, three warps per scheduler" form (variant 5).
+// 32x32 eqn / costgrad, "ping-pong" form (variant 6): one orbit per warp with all state in registers, 8 warps per SM as in
+// ks_warp32x1.cuh, but the two warps of every SM scheduler take turns on the fp64 pipe.
 //
-// Same mathematics, lane mapping, tile layout and scalings as ks_warp32x1.cuh (reference orbithunter/ks/orbits.py: eqn
-// :526-555, costgrad :757-791, rmatvec :711-755 with _rmatvec_parameters :1984-2024 / Relative :3059-3094, precondition
-// :1034-1089), but built for 12 resident warps per SM instead of 8.  profiles/r01s_ncu_full_x1_costgrad32_summary.txt
-// shows why: with two warps per scheduler the fp64 pipe is 57-63 % busy -- each warp spends half of an evaluation in
-// phases that do not feed the pipe (shared-memory exchanges, scoreboard waits), and a single partner warp cannot cover
-// them.  A third warp per scheduler needs <= 168 registers per thread, so
-//   * the field row u(t, .) is kept in a lane-private shared-memory stash between phases B and D (16-byte accesses)
-//     instead of 64 registers,
-//   * u's modes are read straight from global memory at the start of phase A (the other warps of the scheduler cover the
-//     latency; the next orbit's lines are prefetched into L2) -- no cp.async landing zone, which also takes a quarter of
-//     the shared-memory traffic away (the crossbar is the second busiest unit of the x1 kernel).
-// Per warp: XB tile 7.5 KB + field stash 8 KB = 15.5 KB -> 12 warps = 186 KB per SM.
+// Why (profiles/r02e_fft_stream_code_size.jsonl, r02d_x3_knockout_decomposition.jsonl, r02b ncu of variant 5): one fully
+// unrolled evaluation is 2 800 instructions = 45 KB of code, more than the SM's instruction cache serves at full rate.  The
+// same register-resident transforms plus shared-memory exchange reach 98 % of the measured fp64 peak as a 7 KB or 36 KB loop
+// but 64 % as a 57 KB loop (tools/fft_stream.cu) -- exactly where ks_warp32x1.cuh (8 warps) and ks_warp32x3.cuh (12 warps)
+// are stuck: free-running warps drift apart and together walk over the whole 45 KB all the time.  Rolling the phases into
+// loops costs more in register shuffles than it saves (round 1, and variant "p" of this round).
+//
+// Here the eight warps form two groups (warps 0-3 and 4-7: one warp of each group per scheduler).  An evaluation is a
+// chain of "compute chunks" (the register-resident transforms and the pointwise algebra: phases A..E) separated by
+// "exchange chunks" (tile stores, __syncwarp, tile loads, global stores).  A token passed through two named barriers lets
+// exactly one group run its compute chunk while the other group runs its exchange chunk:
+//   group 0:                compute; bar.arrive(1); exchange; bar.sync(2); compute; ...
+//   group 1:  bar.sync(1);  compute; bar.arrive(2); exchange; bar.sync(1); compute; ...
+// so (i) the fp64 pipe of a scheduler always has one warp streaming FMAs at full rate (a single warp's FFT stream reaches
+// 99 % of the pipe, tools/fft_stream.cu kind 0 at 4 warps/SM) while the partner's shared-memory traffic is hidden behind
+// it, and (ii) the groups stay one chunk apart in the code, so the instruction working set is two chunks (< 16 KB).
+// The barriers carry no data dependence (tiles are private to a warp); every warp of a CTA runs the same number of
+// loop trips so that the barrier counts match (idle trips only pass the token on).
+// Mathematics, scalings and the lane mapping are those of ks_warp32x1.cuh (reference orbithunter/ks/orbits.py: eqn
+// :526-555, costgrad :757-791, rmatvec :711-755, _rmatvec_parameters :1984-2024 / Relative :3059-3094, precondition
+// :1034-1089).
 #pragma once
 #include "ks_warp32x1.cuh"
 
-namespace ksx3 {
+namespace kspp {
 using ks::static_for;
 using ksx1::irfft32;
 using ksx1::rfft32_fwd;
 using ksx1::warp_sum;
 
-constexpr int kWarpsPerCta = 12;
-constexpr int kTileDoubles = ksx1::kTileDoubles;  // 960
-constexpr int kStashDoubles = 32 * 32;             // field row of every lane, as 16 double2 per lane
-constexpr int kWarpSmemDoubles = kTileDoubles + kStashDoubles;
+constexpr int kWarpsPerCta = 8;
+constexpr int kTileDoubles = ksx1::kTileDoubles;    // 960
+constexpr int kStageDoubles = ksx1::kStageDoubles;  // cp.async landing zone of the next orbit's half tuples
+constexpr int kWarpSmemDoubles = kTileDoubles + kStageDoubles;
 constexpr int kSmemBytes = kWarpsPerCta * kWarpSmemDoubles * 8;
 
-KS_DEVI void prefetch_l2(const void* p) {
+KS_DEVI void bar_sync(int id) {
 #ifndef KS_HOST_EMUL
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  asm volatile("barrier.sync.aligned %0, 256;" ::"r"(id) : "memory");
 #else
-  (void)p;
+  (void)id;
+#endif
+}
+KS_DEVI void bar_arrive(int id) {
+#ifndef KS_HOST_EMUL
+  asm volatile("barrier.arrive.aligned %0, 256;" ::"r"(id) : "memory");
+#else
+  (void)id;
 #endif
 }
 
 template <int CLS, int OP, bool PC>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x3_kernel(const KsEvalArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32pp_kernel(const KsEvalArgs a) {
   static_assert(OP == KS_OP_EQN || OP == KS_OP_COSTGRAD, "eqn and costgrad");
   constexpr bool GRAD = (OP == KS_OP_COSTGRAD);
   constexpr bool FULL = (CLS == KS_ORBIT || CLS == KS_RELATIVE);
@@ -45,55 +62,82 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x3_kernel(const
   KS_DYN_SMEM(double, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* tile = smem + warp * kWarpSmemDoubles;  // tile[(t * 15 + c) * 2 + component]
-  double2* stash = reinterpret_cast<double2*>(tile + kTileDoubles) + lane;  // pair pr of this lane's row at stash[pr * 32]
+  double* stage = tile + kTileDoubles + lane;     // slot s of this lane at stage[s * 32]
   const int c = lane >> 1, h = lane & 1;
   const bool colact = c < 15;
   const int cc = colact ? c : 14;
-  const bool presE = FULL || h == 1;                                   // half tuple present at even time index
+  const bool presE = FULL || h == 1;                                        // half tuple present at even time index
   const bool presO = FULL || (CLS == KS_ANTISYMMETRIC ? h == 1 : h == 0);  // ... at odd time index
   const int gw = warp * gridDim.x + blockIdx.x, nw = gridDim.x * kWarpsPerCta;  // warp-major (see ks_warp32x1.cuh)
   const bool fix_t = a.cmask & KS_FIX_T, fix_x = a.cmask & KS_FIX_X, fix_s = (a.cmask & KS_FIX_S) || !REL;
   constexpr double cN = 0.5 / (64.0 * 4096.0), cP = 1.0 / (64.0 * 4096.0);
   const int coff = (FULL ? h * 15 : 0) + cc;
   const double q_unit = (cc + 1) * (1.0 / 32.0);
-
-  // Phase boundary.  lockstep = 0: __syncwarp (the tile is private to the warp).  lockstep = 1 (ks_debug_warp32_pingpong):
-  // a named barrier over the three warps that share this SM scheduler (warps w, w + 4, w + 8), so that they walk through the
-  // 45 KB of straight-line code together and one instruction fetch stream serves all three (profiles/r02e: a stream that
-  // does not loop inside the instruction cache is delivered at 0.33 - 0.47 instructions per clock per scheduler).
-  const bool lockstep = a.pingpong != 0;
-  const int trips = lockstep ? (a.batch - (int)blockIdx.x + nw - 1) / nw : 0;  // CTA-uniform trip count (warp 0's)
-  auto phase_sync = [&]() {
-#ifndef KS_HOST_EMUL
-    if (lockstep) asm volatile("barrier.sync.aligned %0, 96;" ::"r"(1 + (warp & 3)) : "memory");
-    else
-#endif
-      __syncwarp();
+  // ---- the token: group 0 = warps 0-3, group 1 = warps 4-7; barrier 1 releases group 1, barrier 2 releases group 0 ----
+  const int group = warp >> 2;
+  const int my_bar = group ? 1 : 2, other_bar = group ? 2 : 1;
+  const bool pp = a.pingpong == 1;
+  const bool pair_lockstep = a.pingpong == 2;  // tuning: the two warps of a scheduler start every compute chunk together
+  // warp 0 of the CTA owns the lowest orbit index, so its trip count is the CTA's maximum; everybody runs that many trips
+  const int trips = (a.batch - (int)blockIdx.x + nw - 1) / nw;
+  constexpr int kChunks = (OP == KS_OP_EQN) ? 3 : 5;
+  int chunks_left = trips * kChunks;  // compute chunks this warp still has to take the token for
+  auto release = [&]() {  // end of a compute chunk: hand the token to the other group
+    if (pp) bar_arrive(other_bar);
   };
-  ks_pdl_launch_dependents();
-  ks_pdl_wait();
-  if (a.stagger_ns > 0 && warp >= 4) ks_nanosleep((unsigned)(a.stagger_ns * (warp >> 2)));  // tuning (ks_debug_warp32_stagger)
-  if (gw < a.batch) prefetch_l2(reinterpret_cast<const char*>(a.modes + (size_t)gw * NM) + lane * 256);
-#pragma unroll 1
-  for (int orbit = gw, trip = 0; lockstep ? trip < trips : orbit < a.batch; orbit += nw, ++trip) {
-    if (orbit >= a.batch) {  // lockstep only: idle trip of the uneven tail, keep the scheduler's barrier count in step
-#pragma unroll 1
-      for (int k = 0; k < (OP == KS_OP_EQN ? 3 : 5); ++k) phase_sync();
-      continue;
-    }
-    // ---------------- phase A (COL): half tuples of u -> A[t] or B[t] -> tile component h ----------------
-    double m1[16], m2[16];  // half tuples (x1, x2) of u; overwritten by F in stage 1
-    {
-      const double* Mn = a.modes + (size_t)orbit * NM + coff;
+  auto acquire = [&]() {  // before a compute chunk; the very last wait of group 1 has no matching release
+    --chunks_left;
+    if (pp && !(group == 1 && chunks_left == 0)) bar_sync(my_bar);
+#ifndef KS_HOST_EMUL
+    if (pair_lockstep) asm volatile("barrier.sync.aligned %0, 64;" ::"r"(3 + (warp & 3)) : "memory");
+#endif
+  };
+
+  auto prefetch = [&](int orb) {  // this lane's half tuples of orbit `orb` -> its stage slots (cp.async, 8 bytes each)
+    if (orb < a.batch) {
+      const double* Mn = a.modes + (size_t)orb * NM + coff;
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
         const bool pres = (J & 1) ? presO : presE;
-        m1[J] = pres ? Mn[J * COLS] : 0.0;
-        if constexpr (J > 0) m2[J] = pres ? Mn[(15 + J) * COLS] : 0.0; else m2[J] = 0.0;
+        if (pres) {
+          ksw32::cp_async8(stage + (J == 0 ? 0 : 2 * J - 1) * 32, Mn + J * COLS);
+          if constexpr (J > 0) ksw32::cp_async8(stage + (2 * J) * 32, Mn + (15 + J) * COLS);
+        }
       });
-      if (orbit + nw < a.batch && lane * 256 < NM * 8)
-        prefetch_l2(reinterpret_cast<const char*>(a.modes + (size_t)(orbit + nw) * NM) + lane * 256);
     }
+    ksw32::cp_async_commit();
+  };
+
+  ks_pdl_launch_dependents();
+  ks_pdl_wait();
+  prefetch(gw);
+  if (pp && group == 1) bar_sync(my_bar);  // group 0 computes first
+#pragma unroll 1
+  for (int trip = 0, orbit = gw; trip < trips; ++trip, orbit += nw) {
+    if (orbit >= a.batch) {  // idle trip (uneven tail of the batch): keep the token moving
+#pragma unroll 1
+      for (int k = 0; k < kChunks; ++k) {
+        release();
+        acquire();
+      }
+      continue;
+    }
+    const double T = a.params[orbit * 3 + 0], Lx = a.params[orbit * 3 + 1], S = a.params[orbit * 3 + 2];
+    const double wbase = -1.0 * (ks::kTwoPi * 32.0 / T);
+    const double q = (ks::kTwoPi * 32.0 / Lx) * q_unit;
+    const double q2 = q * q, q4 = q2 * q2, d = q4 - q2;
+    const double sgq = h ? q : -q;  // d/dx: a' = -q b, b' = +q a
+    const double sig = REL ? S / T : 0.0;
+    // ---------------- phase A (COL): half tuples of u -> A[t] or B[t] -> tile component h ----------------
+    double m1[16], m2[16];  // half tuples (x1, x2) of u; overwritten by F in stage 1
+    ksw32::cp_async_wait<0>();
+    static_for<0, 16>([&](auto Jc) {
+      constexpr int J = decltype(Jc)::value;
+      const bool pres = (J & 1) ? presO : presE;
+      m1[J] = pres ? stage[(J == 0 ? 0 : 2 * J - 1) * 32] : 0.0;
+      if constexpr (J > 0) m2[J] = pres ? stage[(2 * J) * 32] : 0.0; else m2[J] = 0.0;
+    });
+    prefetch(orbit + nw);
     {
       double x[32];
       double hr[16], hi[16];
@@ -104,13 +148,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x3_kernel(const
       }
       hr[0] = hi[0] = 0.0;
       irfft32(ks::kSqrt2 * m1[0], hr, hi, x);
+      release();
       if (colact) {
 #pragma unroll
         for (int t = 0; t < 32; ++t) tile[(t * 15 + c) * 2 + h] = x[t];
       }
     }
-    phase_sync();
-    // ---------------- phase B (ROW): row `lane` -> 64 u -> stash; square -> forward -> tile ----------------
+    __syncwarp();
+    // ---------------- phase B (ROW): row `lane` -> 64 u -> keep; square -> forward -> tile ----------------
+    double U[32];
     {
       double hr[16], hi[16];
       const double2* row = reinterpret_cast<const double2*>(tile) + lane * 15;
@@ -121,33 +167,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x3_kernel(const
         hi[k] = v.y;
       }
       hr[0] = hi[0] = 0.0;
-      double U[32];
+      acquire();
       irfft32(0.0, hr, hi, U);
+      double s[32];
 #pragma unroll
-      for (int pr = 0; pr < 16; ++pr) stash[pr * 32] = make_double2(U[2 * pr], U[2 * pr + 1]);
-#pragma unroll
-      for (int x = 0; x < 32; ++x) U[x] = U[x] * U[x];
+      for (int x = 0; x < 32; ++x) s[x] = U[x] * U[x];
       double c0;
-      rfft32_fwd(U, c0, hr, hi);
+      rfft32_fwd(s, c0, hr, hi);
+      release();
       double2* wrow = reinterpret_cast<double2*>(tile) + lane * 15;
 #pragma unroll
       for (int k = 1; k < 16; ++k) wrow[k - 1] = make_double2(hr[k], hi[k]);
     }
-    phase_sync();
+    __syncwarp();
     // ---------------- phase C (COL): N = 1/2 Dx(.) via the other component; stage 1; W = Dx F via the store ----------------
     {
-      // per-orbit scalars are recomputed in the phases that use them (C and E) from a fresh load of (T, L, S): nothing
-      // but the half tuples stays live across the row phases, which is what keeps the kernel inside 168 registers
-      const double T = a.params[orbit * 3 + 0], Lx = a.params[orbit * 3 + 1], S = a.params[orbit * 3 + 2];
-      const double wbase = -1.0 * (ks::kTwoPi * 32.0 / T);
-      const double q = (ks::kTwoPi * 32.0 / Lx) * q_unit;
-      const double q2 = q * q, q4 = q2 * q2, d = q4 - q2;
-      const double sgq = h ? q : -q;  // d/dx: a' = -q b, b' = +q a
-      const double sig = REL ? S / T : 0.0;
       double x[32];
       const double scl = 4.0 * sgq * cN;
 #pragma unroll
-      for (int t = 0; t < 32; ++t) x[t] = scl * tile[(t * 15 + cc) * 2 + (1 - h)];
+      for (int t = 0; t < 32; ++t) x[t] = tile[(t * 15 + cc) * 2 + (1 - h)];
+      acquire();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) x[t] *= scl;
       double n0, nr[16], ni[16];
       rfft32_fwd(x, n0, nr, ni);
       nr[0] = (0.5 * ks::kSqrt2) * n0;
@@ -220,7 +261,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x3_kernel(const
         }
       }
       if constexpr (OP == KS_OP_EQN) {
-        phase_sync();
+        release();
+        __syncwarp();
+        acquire();  // the next trip's phase A
         continue;
       }
       double hr[16], hi[16];
@@ -234,13 +277,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x3_kernel(const
       // Dx F = iq (A_F + i B_F): h0 writes q A_F to .y, h1 writes -q B_F to .x.  The power-of-two normalisation of the
       // second product (4 cP, applied by ks_warp32x1.cuh when phase E reads the tile) rides on this multiplication.
       const double sw = (h ? -q : q) * (4.0 * cP);
+#pragma unroll
+      for (int t = 0; t < 32; ++t) x[t] *= sw;
+      release();
       if (colact) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) tile[(t * 15 + c) * 2 + (1 - h)] = sw * x[t];
+        for (int t = 0; t < 32; ++t) tile[(t * 15 + c) * 2 + (1 - h)] = x[t];
       }
     }
-    phase_sync();
-    // ---------------- phase D (ROW): second field times u (from the stash) -> forward -> tile ----------------
+    __syncwarp();
+    // ---------------- phase D (ROW): second field times u -> forward -> tile ----------------
     {
       double hr[16], hi[16];
       const double2* row = reinterpret_cast<const double2*>(tile) + lane * 15;
@@ -251,41 +297,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x3_kernel(const
         hi[k] = v.y;
       }
       hr[0] = hi[0] = 0.0;
+      acquire();
       double w[32];
       irfft32(0.0, hr, hi, w);
 #pragma unroll
-      for (int pr = 0; pr < 16; ++pr) {
-        const double2 uu = stash[pr * 32];
-        w[2 * pr] *= uu.x;
-        w[2 * pr + 1] *= uu.y;
-      }
+      for (int x = 0; x < 32; ++x) w[x] *= U[x];
       double c0;
       rfft32_fwd(w, c0, hr, hi);
+      release();
       double2* wrow = reinterpret_cast<double2*>(tile) + lane * 15;
 #pragma unroll
       for (int k = 1; k < 16; ++k) wrow[k - 1] = make_double2(hr[k], hi[k]);
     }
-    phase_sync();
+    __syncwarp();
     // ---------------- phase E (COL): stage 2: grad = -F_t + F_xx + F_xxxx [+ (S/T) F_x] - T(Fx(u w)) ----------------
     {
-      const double T = a.params[orbit * 3 + 0], Lx = a.params[orbit * 3 + 1], S = a.params[orbit * 3 + 2];
-      const double wbase = -1.0 * (ks::kTwoPi * 32.0 / T);
-      const double q = (ks::kTwoPi * 32.0 / Lx) * q_unit;
-      const double q2 = q * q, q4 = q2 * q2, d = q4 - q2;
-      const double sgq = h ? q : -q;  // d/dx: a' = -q b, b' = +q a
-      const double sig = REL ? S / T : 0.0;
       double x[32];
 #pragma unroll
       for (int t = 0; t < 32; ++t) x[t] = tile[(t * 15 + cc) * 2 + h];
+      acquire();
       double p0, pr[16], pi[16];
       rfft32_fwd(x, p0, pr, pi);
       pr[0] = (0.5 * ks::kSqrt2) * p0;
       pi[0] = 0.0;
-      const int out_ld = a.out_ld ? a.out_ld : NM;
-      double* Op = a.out_state + (size_t)orbit * out_ld + coff;
+      double g1v[16], g2v[16];
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
-        const bool pres = (J & 1) ? presO : presE;
         const double w = (J == 0) ? 0.0 : wbase * (J * (1.0 / 32.0));
         const double f1 = m1[J], f2 = m2[J];
         double g1 = fma(d, f1, fma(w, f2, -pr[J]));
@@ -300,14 +337,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x3_kernel(const
           g1 *= pm;
           g2 *= pm;
         }
+        g1v[J] = g1;
+        g2v[J] = g2;
+      });
+      release();
+      const int out_ld = a.out_ld ? a.out_ld : NM;
+      double* Op = a.out_state + (size_t)orbit * out_ld + coff;
+      static_for<0, 16>([&](auto Jc) {
+        constexpr int J = decltype(Jc)::value;
+        const bool pres = (J & 1) ? presO : presE;
         if (colact && pres) {
-          Op[J * COLS] = g1;
-          if constexpr (J > 0) Op[(15 + J) * COLS] = g2;
+          Op[J * COLS] = g1v[J];
+          if constexpr (J > 0) Op[(15 + J) * COLS] = g2v[J];
         }
       });
     }
-    phase_sync();  // the tile is rewritten by the next orbit's phase A (other lanes' columns are read in phase E)
+    __syncwarp();  // the tile is rewritten by the next orbit's phase A (other lanes' columns are read in phase E)
+    acquire();     // the next trip's phase A (or the end of the token chain)
   }
 }
 
-}  // namespace ksx3
+}  // namespace kspp

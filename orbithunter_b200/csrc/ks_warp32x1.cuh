@@ -225,6 +225,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
   // that kernel's writes are visible
   ks_pdl_launch_dependents();
   ks_pdl_wait();
+  // the warps of one scheduler (warp index / 4 = 0, 1, 2) start `stagger_ns` apart: identical work per orbit otherwise keeps
+  // them in the same phase for the whole launch, so the fp64 pipe idles while all of them exchange data and vice versa
+  if (a.stagger_ns > 0 && warp >= 4) ks_nanosleep((unsigned)(a.stagger_ns * (warp >> 2)));
   Pending next{0, 0, 0.0, 1.0, 1.0, 0.0};
   if constexpr (!ADJM) {
     next = decide(gw);

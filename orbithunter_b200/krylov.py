@@ -1,8 +1,8 @@
-"""Newton-Krylov methods of hunt() on the device: 'gmres', 'lsqr' and the matrix-free 'newton_descent' / 'lstsq'.
+"""Newton-Krylov methods of hunt() on the device: 'gmres', 'lsqr', 'lsmr' and the matrix-free 'newton_descent' / 'lstsq'.
 
 Reference: orbithunter/optimize.py _scipy_sparse_linalg_solver_wrapper :1196-1404 (+ _sparse_linalg_factory :1682-1850)
 and _newton_descent :653-852.  ``scipy_kwargs`` keeps SciPy's names: gmres -> restart, maxiter (restart cycles), rtol,
-atol; lsqr -> atol, btol, conlim, iter_lim (damp must be 0).
+atol; lsqr -> atol, btol, conlim, iter_lim (damp must be 0); lsmr -> atol, btol, conlim, maxiter (damp 0, no x0).
 """
 from __future__ import annotations
 
@@ -43,6 +43,16 @@ def newton_krylov(orb: BatchedOrbitKS, method="gmres", tol=1e-6, ftol=1e-9, maxi
             raise NotImplementedError("lsqr damp != 0 is not provided on the device path")
         inner = sk.pop("iter_lim", None)
         inner = 2 * N if inner is None else int(inner)
+        rtol, atol, btol, conlim = 0.0, float(sk.pop("atol", 1e-6)), float(sk.pop("btol", 1e-6)), float(sk.pop("conlim", 1e8))
+        preconditioning = False  # the reference never preconditions lsqr/lsmr (optimize.py:1317-1321)
+    elif method == "lsmr":
+        mid, restart = 2, 1
+        if sk.pop("damp", 0.0):
+            raise NotImplementedError("lsmr damp != 0 is not provided on the device path")
+        if sk.pop("x0", None) is not None:
+            raise NotImplementedError("lsmr x0 is not provided on the device path")
+        inner = sk.pop("maxiter", None)
+        inner = min(N, out.state.shape[1] * out.state.shape[2]) if inner is None else int(inner)  # lsmr.py: min(m, n)
         rtol, atol, btol, conlim = 0.0, float(sk.pop("atol", 1e-6)), float(sk.pop("btol", 1e-6)), float(sk.pop("conlim", 1e8))
         preconditioning = False  # the reference never preconditions lsqr/lsmr (optimize.py:1317-1321)
     elif method == "lstsq":

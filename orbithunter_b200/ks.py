@@ -233,18 +233,29 @@ class OrbitKS:
     def dt(self, order=1, array=False, **kwargs):
         if getattr(self, "frame", "comoving") != "comoving":
             raise ValueError(f"Attempting to compute time derivative of {self} in physical reference frame.")
-        back = kwargs.get("return_basis", self.basis)
+        if kwargs.get("inplace", False):  # only the in-place form honours return_basis (:404-420)
+            back = kwargs.get("return_basis", self.basis)
+            self.state = self._host(self._batched().dt(order, return_basis=back).state)
+            self.basis = back
+            return self.state if array else self
         if array:  # the reference returns the modes-basis array in this case (:432-434)
             return self._host(self._batched().dt(order, return_basis="modes").state)
-        return self._new(state=self._host(self._batched().dt(order, return_basis=back).state), basis=back)
+        # not in place: the derivative comes back in the basis of self, whatever return_basis says (:435-440)
+        return self._new(state=self._host(self._batched().dt(order, return_basis=self.basis).state), basis=self.basis)
 
     def dx(self, **kwargs):
         order, array = kwargs.get("order", 1), kwargs.get("array", False)
         half = self._cls_id() in (2, 3)
-        comp = kwargs.get("computation_basis", "spatial_modes" if (half and order % 2) else "modes")
+        comp = kwargs.get("computation_basis", "modes")
         if half and order % 2:
-            comp = "spatial_modes"
+            comp = "spatial_modes"  # odd orders of the discrete-symmetry classes NEED the spatial mode basis (:3222-3224, :3614-3616)
+        if comp not in ("modes", "spatial_modes"):
+            raise ValueError(f"{str(self)}.dx(computation_basis={comp}); invalid basis for spectral differentiation. ")
         back = kwargs.get("return_basis", self.basis)
+        if kwargs.get("inplace", False):
+            self.state = self._host(self._batched().dx(order, comp, return_basis=back).state)
+            self.basis = back
+            return self.state if array else self
         if array:  # array=True returns the derivative in the computation basis (:518-519)
             return self._host(self._batched().dx(order, comp, return_basis=comp).state)
         return self._new(state=self._host(self._batched().dx(order, comp, return_basis=back).state), basis=back)

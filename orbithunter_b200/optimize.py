@@ -1,6 +1,6 @@
 """hunt(): the reference's solver front end (orbithunter/optimize.py:82-364) for single orbits and whole batches.
 
-Methods on the device path: 'adj' (adjoint descent, optimize.py:367-509), 'gmres' and 'lsqr' (Newton-Krylov,
+Methods on the device path: 'adj' (adjoint descent, optimize.py:367-509), 'gmres', 'lsqr' and 'lsmr' (Newton-Krylov,
 optimize.py:1196-1404 with _sparse_linalg_factory :1682-1850), 'newton_descent' (matrix-free restatement of
 :653-852: the pseudo-inverse step -J^+ F is the minimum-norm least-squares solution LSQR converges to from x0 = 0) and
 'lstsq' (:855-1022, without preconditioning; the second stage of BASELINE configs[0]): dense Jacobian by one batched
@@ -25,7 +25,7 @@ from .ks import OrbitKS
 
 __all__ = ["hunt", "OrbitResult"]
 
-_DEVICE_METHODS = ("adj", "gmres", "lsqr", "newton_descent", "lstsq")
+_DEVICE_METHODS = ("adj", "gmres", "lsqr", "lsmr", "newton_descent", "lstsq")
 _MESSAGES = {
     -1: "Has not failed yet: tolerance not met but no exit condition triggered.",
     0: "Failed to converge: minimum backtracking step size reached.",
@@ -100,7 +100,7 @@ def _adjoint_descent(orb: BatchedOrbitKS, tol=1e-6, ftol=1e-9, maxiter=10000, mi
 def _run_method(orb, method, hunt_kwargs):
     if method == "adj":
         return _adjoint_descent(orb, **hunt_kwargs)
-    if method in ("gmres", "lsqr", "newton_descent", "lstsq"):
+    if method in ("gmres", "lsqr", "lsmr", "newton_descent", "lstsq"):
         from .krylov import newton_krylov
 
         return newton_krylov(orb, method=method, **hunt_kwargs)

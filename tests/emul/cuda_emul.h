@@ -113,6 +113,7 @@ using std::fmax;
 using std::fabs;
 using std::sqrt;
 static inline double __ldg(const double* p) { return *p; }
+static inline void ks_nanosleep(unsigned) {}
 static inline void sincospi(double x, double* s, double* c) {
   const long double a = 3.14159265358979323846264338327950288L * (long double)x;
   *s = (double)sinl(a);

@@ -48,7 +48,7 @@ def _check_all_ops(cid, n, m, B, cons):
     assert np.allclose(rp, orp, rtol=1e-11, atol=1e-11 * max(np.max(np.abs(orp)), 1e-300))
 
 
-@pytest.mark.parametrize("variant", [3, 4, 5])
+@pytest.mark.parametrize("variant", [3, 4, 5, 6])
 @pytest.mark.parametrize("cid", range(4))
 def test_warp32_kernel_all_ops(cid, variant):
     E.lib().ks_debug_force_generic(0)

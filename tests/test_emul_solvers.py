@@ -104,3 +104,23 @@ def test_gmres_square_system_when_every_parameter_is_constrained(cid, precond):
         assert (int(status[b]), int(nit[b])) == (st["status"], st["nit"])
         assert abs(cost[b] - st["cost"]) <= 1e-10 * max(1.0, st["cost"])
         assert relerr(Mo[b], rm) < 1e-9 and np.array_equal(po[b], p[b])
+
+
+@pytest.mark.parametrize("cid", [0, 1, 3])
+def test_lsmr_matches_scipy_based_oracle(cid):
+    """hunt('lsmr') (optimize.py:1319-1321): the device LSMR recurrences (SciPy _isolve/lsmr.py restated) vs the oracle,
+    which calls scipy.sparse.linalg.lsmr as the reference does."""
+    n = m = 16
+    B = 2
+    M = np.stack([ko.populate_state(44.0, 44.0, n, m, 3 + s, cid) for s in range(B)])
+    p = np.tile([44.0, 44.0, 0.3 if cid == 1 else 0.0], (B, 1))
+    cons = ko.default_constraints(cid)
+    cmask = sum(1 << i for i in range(3) if cons[i])
+    # 20 Golub-Kahan steps: the trajectories agree to round-off (at 40 steps and N ~ 200 orthogonality is lost and the same
+    # comparison drifts to 3e-6, as it does between SciPy and itself under 1e-15 input noise)
+    Mo, po, status, nit, cost, cnt = E.newton_krylov(cid, n, m, M, p, cmask, 2, maxiter=2, inner=20, atol=1e-6, btol=1e-6)
+    for b in range(B):
+        rm, rp, st = ko.newton_krylov(M[b], p[b], cid, method="lsmr", maxiter=2, scipy_kwargs=dict(maxiter=20))
+        assert (int(status[b]), int(nit[b])) == (st["status"], st["nit"])
+        assert abs(cost[b] - st["cost"]) <= 1e-10 * max(1.0, st["cost"])
+        assert relerr(Mo[b], rm) < 1e-9

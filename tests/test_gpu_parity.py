@@ -157,7 +157,7 @@ def test_warp32_matches_generic_kernel(cid):
     assert relerr(g1.cpu_state(), g2.cpu_state()) < TOL and np.allclose(c1.cpu().numpy(), c2.cpu().numpy(), rtol=1e-13)
 
 
-@pytest.mark.parametrize("variant", [3, 4, 5])
+@pytest.mark.parametrize("variant", [3, 4, 5, 6])
 @pytest.mark.parametrize("cid", range(4))
 def test_warp32_variants_vs_oracle(cid, variant):
     """Every build of the 32x32 eqn / costgrad kernel (two orbits per warp; one orbit per warp with 8 and with 12 warps per

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--batches", default="4096,8192,16384,65536")
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--cls", type=int, default=0)
+    ap.add_argument("--staggers", default="0")
+    ap.add_argument("--pingpong", default="1", help="variant 6: comma list of 0/1")
     args = ap.parse_args()
     L = _lib.lib()
     dev = torch.device("cuda", 0)
@@ -42,8 +44,11 @@ def main():
                                      g.data_ptr(), gp.data_ptr(), None, ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream))
 
         ref = None
-        for v in [int(x) for x in args.variants.split(",")]:
+        for v, stg, pp in [(int(x), int(y), int(z)) for x in args.variants.split(",") for y in args.staggers.split(",")
+                           for z in (args.pingpong.split(",") if int(x) >= 5 else ["0"])]:
             L.ks_debug_warp32_variant(v)
+            L.ks_debug_warp32_pingpong(pp)
+            L.ks_debug_warp32_stagger(stg)
             for i in range(2 * nsets):
                 step(i)
             torch.cuda.synchronize()
@@ -79,12 +84,14 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms_graph = e0.elapsed_time(e1) / (reps * n_g)
-            print(json.dumps({"variant": v, "cls": cls_name, "batch": B, "sets": nsets, "us_plain": 1e3 * ms_plain,
+            print(json.dumps({"variant": v, "stagger_ns": stg, "pingpong": pp, "cls": cls_name, "batch": B, "sets": nsets, "us_plain": 1e3 * ms_plain,
                               "us_graph": 1e3 * ms_graph, "Mevals_plain": B / ms_plain / 1e3, "Mevals_graph": B / ms_graph / 1e3,
                               "hbm_frac_graph": B * 8 * (2 * nm + 7) / (ms_graph * 1e-3) / 6451.2e9,
                               "rel_diff_vs_first": [abs(chk[0] - ref[0]) / abs(ref[0]), abs(chk[1] - ref[1]) / abs(ref[1])]}),
                   flush=True)
         L.ks_debug_warp32_variant(4)
+        L.ks_debug_warp32_stagger(0)
+        L.ks_debug_warp32_pingpong(0)
         del sets
 
 
