@@ -456,7 +456,7 @@ def normal_operator(modes, params, cls, constraints):
 
 def newton_krylov(modes, params, cls=ORBIT, constraints=None, method="gmres", tol=1e-6, ftol=1e-9, maxiter=10000,
                   min_step=1e-6, preconditioning=False, scipy_kwargs=None):
-    """optimize.py:1196-1404 for ONE orbit with method in {gmres, lsqr, lsmr}; inner solver is SciPy's, as in the reference."""
+    """optimize.py:1196-1404 for ONE orbit with method in {gmres, lsqr, lsmr, lstsq}; inner solver is SciPy's, as in the reference."""
     from scipy.sparse.linalg import LinearOperator, gmres, lsmr, lsqr
 
     constraints = default_constraints(cls) if constraints is None else constraints
@@ -470,7 +470,18 @@ def newton_krylov(modes, params, cls=ORBIT, constraints=None, method="gmres", to
     while c > tol and stats["status"] == -1:
         step = 1.0
         N = cdof(modes, params, constraints).size
-        if method in ("lsqr", "lsmr"):
+        if method == "lstsq":
+            # optimize.py:855-1022 (no preconditioning): dense Jacobian (ks/orbits.py:557-657), scipy.linalg.lstsq
+            from scipy.linalg import lstsq as _dense_lstsq
+
+            Jd = np.empty((modes.size, N))
+            for col in range(N):
+                e = np.zeros(N)
+                e[col] = 1.0
+                vs, vp = from_cdof(e, shape, constraints)
+                Jd[:, col] = matvec(modes, params, vs, vp, cls, constraints).ravel()
+            x = _dense_lstsq(Jd, -1.0 * eqn(modes, params, cls).ravel())[0]
+        elif method in ("lsqr", "lsmr"):
             def mv(v):
                 vs, vp = from_cdof(np.asarray(v).ravel(), shape, constraints)
                 return matvec(modes, params, vs, vp, cls, constraints).ravel()

@@ -32,6 +32,9 @@ _SIG = {
     "ks_newton_krylov": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_uint32, C.c_int, C.c_double, C.c_double,
                                    C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                    C.c_double, _P, _P, _P, C.POINTER(C.c_longlong), C.c_int, _P, C.c_size_t, _P]),
+    "ks_newton_dense_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ks_newton_dense": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_uint32, C.c_double, C.c_double, C.c_int,
+                                  C.c_double, C.c_int, C.c_int, _P, _P, _P, C.POINTER(C.c_longlong), _P, C.c_size_t, _P]),
 }
 
 EXPORTS = tuple(_SIG)

@@ -2,10 +2,13 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <vector>
 
 #include "../../include/ks_b200.h"
 #include "ks_adjoint.cuh"
 #include "ks_common.cuh"
+#include "ks_dense.cuh"
+#include "ks_dense_host.cuh"
 #include "ks_generic.cuh"
 #include "ks_krylov.cuh"
 #include "ks_host.cuh"
@@ -536,6 +539,40 @@ struct NkLayout {
   size_t off[24];
 };
 // carve sizes shared by the _workspace_bytes query and the driver
+// dense Newton step (method 3): sizes of the per-chunk buffers, shared by the workspace query and the driver
+struct DenseLayout {
+  size_t total;
+  size_t off[16];
+};
+DenseLayout dense_layout(int cls, int n, int m, int batch, int chunk) {
+  const size_t nm = (size_t)(n - 1) * mode_cols(cls, m), N = nm + 3, C = (size_t)chunk;
+  const size_t nblk = (nm + ksd::kNb - 1) / ksd::kNb;
+  DenseLayout L;
+  size_t p = 0;
+  int k = 0;
+  auto take = [&](size_t bytes) {
+    L.off[k++] = p;
+    p += align256(bytes);
+  };
+  take((size_t)batch * 4);                                 // 0 live list (device copy)
+  take(C * nm * 8);                                        // 1 U chunk
+  take(C * 3 * 8);                                         // 2 P chunk
+  take(C * nm * 8);                                        // 3 rhs chunk (-F)
+  take(C * nm * 8);                                        // 4 residual / right-hand side of the current solve
+  take(C * nm * 8);                                        // 5 y
+  take(C * N * 8);                                         // 6 dx chunk
+  take(C * N * 3 * 8);                                     // 7 parameters replicated per Jacobian column
+  take(C * nm * N * 8);                                    // 8 J (column-major Nm x N per orbit)
+  take(C * N * N * 8);                                     // 9 G = J J^T (also: the identity the Jacobian is built from)
+  take(C * N * N * 8);                                     // 10 L (also: the orbit replicated per Jacobian column)
+  take(C * nblk * ksd::kNb * ksd::kNb * 8);                // 11 inverted diagonal blocks
+  take(C * 8);                                             // 12 lambda
+  take(C * 8);                                             // 13 mean diagonal of G
+  take(C * 4 + 256);                                       // 14 fail flags + redo counter
+  take(ks_workspace_bytes(cls, n, m, (int)(C * N)));       // 15 evaluation workspace of the Jacobian build
+  L.total = p;
+  return L;
+}
 NkLayout nk_layout(int cls, int n, int m, int batch, int method, int restart, uint32_t cmask) {
   const size_t nm = (size_t)(n - 1) * mode_cols(cls, m);
   const size_t N = nm + 3;  // upper bound on cdof (3 free parameters)
@@ -567,6 +604,9 @@ NkLayout nk_layout(int cls, int n, int m, int batch, int method, int restart, ui
     take((size_t)batch * restart * (restart + 1) * 8);        // 16 H
     take((size_t)batch * restart * 2 * 8);                    // 17 Givens
     take((size_t)batch * (restart + 1) * 8);                  // 18 S
+  } else if (method == 3) {
+    take(dense_layout(cls, n, m, batch, restart).total);      // 15 dense region (`restart` carries the chunk size)
+    take(8); take(8); take(8);                                // 16-18 unused
   } else {
     take(batch * nm * 8);                                     // 15 u
     take(batch * N * 8);                                      // 16 v
@@ -583,13 +623,17 @@ size_t ks_newton_krylov_workspace_bytes(int cls, int n, int m, int batch, int me
   return nk_layout(cls, n, m, batch, method, restart, 0).total;
 }
 
-int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* params, uint32_t cmask, int method,
-                     double tol, double ftol, int maxiter, double min_step, int preconditioning, int restart,
-                     int inner_maxiter, double rtol, double atol, double btol, double conlim, int32_t* status_out,
-                     int32_t* nit_out, double* cost_out, long long* counters_out, int check_every, void* ws,
-                     size_t ws_bytes, void* stream) {
+}  // extern "C"
+namespace {
+// Outer Newton loop shared by ks_newton_krylov (methods 0-2) and ks_newton_dense (method 3, `restart` = chunk size,
+// `inner_maxiter` = refinement steps).
+int newton_driver(int cls, int n, int m, int batch, double* modes, double* params, uint32_t cmask, int method,
+                  double tol, double ftol, int maxiter, double min_step, int preconditioning, int restart,
+                  int inner_maxiter, double rtol, double atol, double btol, double conlim, int32_t* status_out,
+                  int32_t* nit_out, double* cost_out, long long* counters_out, int check_every, void* ws,
+                  size_t ws_bytes, void* stream) {
   if (!shape_ok(cls, n, m)) return fail(KS_ERR_SHAPE, "unsupported class / discretization (need even n, m >= 4)");
-  if (batch < 0 || maxiter < 0 || method < 0 || method > 2) return fail(KS_ERR_ARG, "bad batch / maxiter / method");
+  if (batch < 0 || maxiter < 0 || method < 0 || method > 3) return fail(KS_ERR_ARG, "bad batch / maxiter / method");
   if (counters_out) counters_out[0] = counters_out[1] = counters_out[2] = counters_out[3] = 0;
   if (batch == 0) return 0;
   if (!modes || !params || !status_out || !nit_out || !cost_out) return fail(KS_ERR_ARG, "null array argument");
@@ -651,6 +695,110 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
     return dispatch<KS_OP_RMATVEC>(cls, n, m, a, eval_ws, eval_bytes, stream);
   };
 
+  // ---- method 3: the dense least-squares step for the `n_live` orbits still in the loop (ks_dense.cuh), chunk by chunk ----
+  std::vector<int> h_live, h_idx;
+  int rc_dense = 0;
+  auto dense_step = [&](int n_live) -> int {
+    const int chunk = restart, refine = inner_maxiter;
+    const DenseLayout dl = dense_layout(cls, n, m, batch, chunk);
+    unsigned char* db = at(15);
+    auto dat = [&](int k) { return db + dl.off[k]; };
+    int* d_idx = reinterpret_cast<int*>(dat(0));
+    double* Uc = reinterpret_cast<double*>(dat(1));
+    double* Pc = reinterpret_cast<double*>(dat(2));
+    double* rhs0 = reinterpret_cast<double*>(dat(3));
+    double* res = reinterpret_cast<double*>(dat(4));
+    double* yv = reinterpret_cast<double*>(dat(5));
+    double* dxc = reinterpret_cast<double*>(dat(6));
+    double* Prep = reinterpret_cast<double*>(dat(7));
+    double* J = reinterpret_cast<double*>(dat(8));
+    double* G = reinterpret_cast<double*>(dat(9));
+    double* Lf = reinterpret_cast<double*>(dat(10));
+    double* Li = reinterpret_cast<double*>(dat(11));
+    double* lambda = reinterpret_cast<double*>(dat(12));
+    double* gmean = reinterpret_cast<double*>(dat(13));
+    int* failf = reinterpret_cast<int*>(dat(14));
+    int* redo = failf + chunk;
+    void* jws = dat(15);
+    const size_t jws_bytes = ks_workspace_bytes(cls, n, m, chunk * N);
+    // live list: flags to the host (the driver has just synchronised on the live count), indices back
+    h_live.resize(batch);
+    if (cudaMemcpyAsync(h_live.data(), live, (size_t)batch * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+      return fail(KS_ERR_LAUNCH, "dense Newton step: reading the live flags failed");
+    h_idx.clear();
+    for (int b = 0; b < batch; ++b)
+      if (h_live[b]) h_idx.push_back(b);
+    if ((int)h_idx.size() != n_live) return fail(KS_ERR_LAUNCH, "dense Newton step: live list out of step");
+    if (cudaMemcpyAsync(d_idx, h_idx.data(), h_idx.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return fail(KS_ERR_LAUNCH, "dense Newton step: writing the live list failed");
+    const int nblk = (nm + ksd::kNb - 1) / ksd::kNb;
+    const long long sJ = (long long)nm * N, sG = (long long)nm * nm, sLi = (long long)nblk * ksd::kNb * ksd::kNb;
+    static DynSmemOptIn diag_optin;
+    if (!diag_optin.ensure(ksd::chol_diag_kernel, ksd::kDiagSmemBytes)) return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(chol_diag) failed");
+    const size_t vec_smem = (size_t)(nm + ksd::kNb) * 8, x_smem = (size_t)N * 8;
+    for (int c0 = 0; c0 < n_live; c0 += chunk) {
+      const int C = n_live - c0 < chunk ? n_live - c0 : chunk;
+      const int* idx = d_idx + c0;
+      KS_LAUNCH(ksd::gather_kernel, C, 256, 0, s, idx, (const double*)modes, (const double*)params, (const double*)Fy, Uc, Pc, rhs0, nm);
+      // Jacobian: one batched matvec over the identity; column `col` of orbit c is evaluation number c * N + col
+      double* Urep = Lf;
+      double* Vrep = G;
+      KS_LAUNCH(ksd::replicate_kernel, 1184, 256, 0, s, (const double*)Uc, Urep, nm, N, (size_t)C * N * nm);
+      KS_LAUNCH(ksd::replicate_kernel, 296, 256, 0, s, (const double*)Pc, Prep, 3, N, (size_t)C * N * 3);
+      KS_LAUNCH(ksd::identity_kernel, 1184, 256, 0, s, Vrep, N, (size_t)C * N * N);
+      {
+        KsEvalArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.modes = Urep; a.params = Prep; a.vmodes = Vrep; a.vparams = nullptr; a.out_state = J; a.batch = C * N;
+        a.cmask = cmask; a.v_ld = N; a.v_tail = 1;
+        n_ops += N;
+        if ((rc_dense = dispatch<KS_OP_MATVEC>(cls, n, m, a, jws, jws_bytes, stream)) != 0) return rc_dense;
+      }
+      // G = J J^T, then G (+ lambda I) = L L^T; orbits whose factorisation breaks down are redone with a growing shift
+      for (int attempt = 0; attempt < 5; ++attempt) {
+        cudaMemsetAsync(redo, 0, 4, s);
+        KS_LAUNCH(ksd::lambda_kernel, (C + 255) / 256, 256, 0, s, (const double*)gmean, lambda, failf, redo, attempt, C);
+        if (attempt > 0) {
+          int n_redo = 0;
+          if (cudaMemcpyAsync(&n_redo, redo, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+            return fail(KS_ERR_LAUNCH, "dense Newton step: device error while checking the factorisation");
+          if (n_redo == 0) break;
+        }
+        if ((rc_dense = ksdh::dgemm_batched(s, false, true, nm, nm, N, 1.0, J, nm, sJ, J, nm, sJ, 0.0, G, nm, sG, C)) != 0) return rc_dense;
+        if (attempt == 0) KS_LAUNCH(ksd::diag_mean_kernel, C, ksd::kThreads, 0, s, (const double*)G, gmean, nm);
+        else KS_LAUNCH(ksd::shift_diag_kernel, C, 256, 0, s, G, (const double*)lambda, nm);
+        for (int blk = 0; blk < nblk; ++blk) {
+          const int k0 = blk * ksd::kNb, b = nm - k0 < ksd::kNb ? nm - k0 : ksd::kNb, k1 = k0 + b, rest = nm - k1;
+          KS_LAUNCH(ksd::chol_diag_kernel, C, ksd::kThreads, ksd::kDiagSmemBytes, s, (const double*)G, Lf, Li, failf, nm, k0, b, blk);
+          if (rest > 0) {
+            // panel: L[k1:, k0:k1] = G[k1:, k0:k1] L_kk^-T ; trailing: G[k1:, k1:] -= L[k1:, k0:k1] L[k1:, k0:k1]^T
+            if ((rc_dense = ksdh::dgemm_batched(s, false, true, rest, b, b, 1.0, G + k1 + (size_t)k0 * nm, nm, sG,
+                                                Li + (size_t)blk * ksd::kNb * ksd::kNb, ksd::kNb, sLi, 0.0, Lf + k1 + (size_t)k0 * nm, nm, sG, C)) != 0)
+              return rc_dense;
+            if ((rc_dense = ksdh::dgemm_batched(s, false, true, rest, rest, b, -1.0, Lf + k1 + (size_t)k0 * nm, nm, sG,
+                                                Lf + k1 + (size_t)k0 * nm, nm, sG, 1.0, G + k1 + (size_t)k1 * nm, nm, sG, C)) != 0)
+              return rc_dense;
+          }
+        }
+      }
+      // dx = J^T (L L^T)^-1 (-F), then `refine` rounds of r = -F - J dx, dx += J^T (L L^T)^-1 r
+      for (int it = 0; it <= refine; ++it) {
+        const double* r = rhs0;
+        if (it > 0) {
+          KS_LAUNCH(ksd::gemv_kernel, C, ksd::kThreads, x_smem, s, (const double*)J, (const double*)dxc, (const double*)rhs0, res, nm, N, 1, 0);
+          r = res;
+        }
+        KS_LAUNCH(ksd::tri_solve_kernel, C, ksd::kThreads, vec_smem, s, (const double*)Lf, (const double*)Li, r, yv, nm);
+        KS_LAUNCH(ksd::gemv_kernel, C, ksd::kThreads, vec_smem, s, (const double*)J, (const double*)yv, (const double*)nullptr, dxc, nm, N, 0,
+                  it > 0 ? 1 : 0);
+      }
+      KS_LAUNCH(ksd::scatter_kernel, C, 256, 0, s, idx, (const double*)dxc, xsol, N);
+      n_steps += C;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "dense Newton step: kernel launch failed");
+  };
+
   // initial cost and loop mask
   int rc = eval_eqn(modes, params, Fy, cost_out);
   if (rc != 0) return rc;
@@ -665,7 +813,9 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
     ++n_outer;
     // right-hand side: -F  (and A^T(-F) for the normal equations)
     if ((rc = eval_eqn(modes, params, Fy, nullptr)) != 0) return rc;
-    if (method == 0) {
+    if (method == 3) {
+      if ((rc = dense_step(n_live)) != 0) return rc;
+    } else if (method == 0) {
       if (square) {  // every parameter constrained: GMRES on J dx = -F itself                     (:1803-1850)
         KS_LAUNCH(kskry::negate_kernel, 296, 256, 0, s, Fy, rhs, (size_t)batch * nm);
       } else {       // normal equations A^T A dx = A^T (-F)                                        (:1764-1797)
@@ -785,6 +935,34 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
     counters_out[0] = n_ops; counters_out[1] = n_steps; counters_out[2] = n_ls; counters_out[3] = n_outer;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "newton-krylov launch failed");
+}
+}  // namespace
+
+extern "C" {
+int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* params, uint32_t cmask, int method,
+                     double tol, double ftol, int maxiter, double min_step, int preconditioning, int restart,
+                     int inner_maxiter, double rtol, double atol, double btol, double conlim, int32_t* status_out,
+                     int32_t* nit_out, double* cost_out, long long* counters_out, int check_every, void* ws,
+                     size_t ws_bytes, void* stream) {
+  if (method < 0 || method > 2) return fail(KS_ERR_ARG, "bad method (0 gmres, 1 lsqr, 2 lsmr)");
+  return newton_driver(cls, n, m, batch, modes, params, cmask, method, tol, ftol, maxiter, min_step, preconditioning, restart,
+                       inner_maxiter, rtol, atol, btol, conlim, status_out, nit_out, cost_out, counters_out, check_every, ws, ws_bytes,
+                       stream);
+}
+
+size_t ks_newton_dense_workspace_bytes(int cls, int n, int m, int batch, int chunk) {
+  if (!shape_ok(cls, n, m) || batch <= 0 || chunk <= 0) return 0;
+  return nk_layout(cls, n, m, batch, 3, chunk, 0).total;
+}
+
+int ks_newton_dense(int cls, int n, int m, int batch, double* modes, double* params, uint32_t cmask, double tol, double ftol,
+                    int maxiter, double min_step, int chunk, int refine, int32_t* status_out, int32_t* nit_out,
+                    double* cost_out, long long* counters_out, void* ws, size_t ws_bytes, void* stream) {
+  if (chunk <= 0 || refine < 0) return fail(KS_ERR_ARG, "dense Newton step: chunk must be positive and refine non-negative");
+  if (shape_ok(cls, n, m) && (size_t)(n - 1) * mode_cols(cls, m) > 5000)
+    return fail(KS_ERR_SHAPE, "dense Newton step: more than 5000 modes per orbit (use the matrix-free methods)");
+  return newton_driver(cls, n, m, batch, modes, params, cmask, 3, tol, ftol, maxiter, min_step, 0, chunk, refine, 0.0, 0.0, 0.0, 0.0,
+                       status_out, nit_out, cost_out, counters_out, 8, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -87,57 +87,35 @@ def newton_krylov(orb: BatchedOrbitKS, method="gmres", tol=1e-6, ftol=1e-9, maxi
 
 
 def _dense_lstsq(orb: BatchedOrbitKS, tol, ftol, maxiter, min_step, preconditioning, **kwargs):
-    """hunt('lstsq') (reference optimize.py:855-1022, the second stage of BASELINE configs[0]), orbit by orbit as the reference
-    does: dense Jacobian (one batched matvec over the identity on the device), dx = the minimum-norm least-squares solution
-    of J dx = -F (the reference calls scipy.linalg.lstsq, LAPACK gelsd with cond = eps; here the SVD pseudo-inverse of
-    torch.linalg on the device with the same cut-off), full step then halving while the cost increases (`>`), and
-    _process_correction (:2115-2239).  Cost O(N^3) per iteration and orbit, like the reference: meant for a handful of
-    orbits; large batches belong to 'lsqr' / 'gmres' / 'newton_descent' (matrix-free)."""
+    """hunt('lstsq') (reference optimize.py:855-1022, the second stage of BASELINE configs[0]) for the whole batch on the
+    device: ks_newton_dense builds the dense Jacobians of the orbits still in the loop with one batched matvec over the
+    identity, takes the minimum-norm solution of J dx = -F (the reference: scipy.linalg.lstsq) as J^T (J J^T)^-1 (-F) through a
+    blocked Cholesky factorisation with iterative refinement, then the reference's line search (full step, halve while the cost
+    increases) and _process_correction (:2115-2239).  ``chunk`` (kwarg, default 256) orbits are factored at a time."""
     if preconditioning:
         raise NotImplementedError("hunt('lstsq', preconditioning=True) (right-preconditioned dense least squares) is not provided")
     if not kwargs.get("backtracking", True):
         min_step = 1
+    if kwargs.get("step_size", 1) != 1:
+        raise NotImplementedError("hunt('lstsq', step_size != 1) is not provided on the device path")
     out = orb.copy()
     B, dev = out.batch, out.state.device
+    L = _lib.lib()
+    chunk = max(1, min(int(kwargs.get("chunk", 256)), B))
+    refine = int(kwargs.get("refine", 2))
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    nit = torch.empty(B, dtype=torch.int32, device=dev)
+    cost = torch.empty(B, dtype=torch.float64, device=dev)
     initial_cost = orb.cost()
-    status = torch.full((B,), -1, dtype=torch.int32, device=dev)
-    nit = torch.zeros(B, dtype=torch.int32, device=dev)
-    cost_out = initial_cost.clone()
-    eps = float(np.finfo(np.float64).eps)
-    for b in range(B):
-        o = out[b]
-        F = o.eqn()
-        cost = F.cost(evaleqn=False)
-        st, it = -1, 0
-        while cost > tol and st == -1:
-            step = kwargs.get("step_size", 1)
-            J = torch.as_tensor(o.jacobian(), device=dev)
-            rhs = torch.as_tensor(-1.0 * F.state.ravel(), device=dev)
-            dx = (torch.linalg.pinv(J, rtol=eps) @ rhs).cpu().numpy()
-            dxo = o.from_numpy_array(dx)
-            nxt = o.increment(dxo, step_size=step)
-            nF = nxt.eqn()
-            ncost = nF.cost(evaleqn=False)
-            while ncost > cost and step > min_step:
-                step /= 2.0
-                nxt = o.increment(dxo, step_size=step)
-                nF = nxt.eqn()
-                ncost = nF.cost(evaleqn=False)
-            it += 1                                                                        # _process_correction
-            if ncost <= tol:
-                st, o, F, cost = -1, nxt, nF, ncost
-            elif step <= min_step:
-                st = 0
-            elif it == int(maxiter):
-                st = 2
-                if ncost < cost:
-                    o, F, cost = nxt, nF, ncost
-            elif (cost - ncost) / max([cost, ncost, 1]) < ftol:
-                st = 3
-            else:
-                o, F, cost = nxt, nF, ncost
-        out.state[b] = torch.as_tensor(o.state, device=dev)
-        out.parameters[b] = torch.as_tensor(np.asarray(o.parameters, dtype=np.float64), device=dev)
-        status[b], nit[b], cost_out[b] = st, it, float(cost)
-    stats = {"method": "lstsq", "nit": nit, "costs": [initial_cost, cost_out], "maxiter": maxiter, "tol": tol, "status": status}
+    nbytes = L.ks_newton_dense_workspace_bytes(out.cls_id, out.n, out.m, B, chunk)
+    ws = workspace(dev, nbytes)
+    counters = (ctypes.c_longlong * 4)()
+    with torch.cuda.device(dev):
+        _lib.check(L.ks_newton_dense(out.cls_id, out.n, out.m, B, out.state.data_ptr(), out.parameters.data_ptr(), out.cmask,
+                                     float(tol), float(ftol), int(maxiter), float(min_step), chunk, refine, status.data_ptr(),
+                                     nit.data_ptr(), cost.data_ptr(), counters, ws.data_ptr(), ws.numel(),
+                                     torch.cuda.current_stream().cuda_stream))
+    stats = {"method": "lstsq", "nit": nit, "costs": [initial_cost, cost], "maxiter": maxiter, "tol": tol, "status": status,
+             "jacobian_columns": counters[0], "dense_solves": counters[1], "line_search_evals": counters[2],
+             "outer_iterations": counters[3]}
     return out, stats

@@ -148,6 +148,22 @@ def newton_krylov(cls, n, m, modes, params, cmask, method, tol=1e-6, ftol=1e-9, 
     return modes, params, status, nit, cost, list(counters)
 
 
+def newton_dense(cls, n, m, modes, params, cmask, tol=1e-6, ftol=1e-9, maxiter=10000, min_step=1e-6, chunk=2, refine=2):
+    L = lib()
+    modes = np.array(modes, dtype=float, order="C")
+    params = np.array(params, dtype=float, order="C")
+    B = modes.shape[0]
+    status = np.zeros(B, dtype=np.int32)
+    nit = np.zeros(B, dtype=np.int32)
+    cost = np.zeros(B)
+    nb = L.ks_newton_dense_workspace_bytes(cls, n, m, B, chunk)
+    ws = np.zeros(nb // 8 + 1)
+    counters = (C.c_longlong * 4)()
+    _chk(L, L.ks_newton_dense(cls, n, m, B, _p(modes), _p(params), cmask, tol, ftol, maxiter, min_step, chunk, refine, _p(status), _p(nit),
+                              _p(cost), counters, _p(ws), nb, None))
+    return modes, params, status, nit, cost, list(counters)
+
+
 def deriv(cls, n, m, arr, params, axis, order):
     L = lib()
     arr = np.ascontiguousarray(arr, dtype=float)

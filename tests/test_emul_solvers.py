@@ -124,3 +124,24 @@ def test_lsmr_matches_scipy_based_oracle(cid):
         assert (int(status[b]), int(nit[b])) == (st["status"], st["nit"])
         assert abs(cost[b] - st["cost"]) <= 1e-10 * max(1.0, st["cost"])
         assert relerr(Mo[b], rm) < 1e-9
+
+
+@pytest.mark.parametrize("cid", [1])
+def test_dense_newton_matches_lstsq_oracle(cid):
+    """hunt('lstsq') on the device (ks_newton_dense: Jacobian by batched matvec, blocked Cholesky of J J^T, refinement) vs the
+    oracle's restatement of optimize.py:855-1022 with scipy.linalg.lstsq: same status / nit, cost to 1e-8 -- two orbits in two
+    chunks (chunk = 1), two Cholesky blocks (110 modes).  (The thread emulation of the 256-thread factorisation kernels is slow;
+    all classes and 16x16 pass the same check in 11 min, and the -m gpu tests cover 32x32.)"""
+    n = m = 12
+    B = 2
+    M = np.stack([ko.populate_state(44.0, 44.0, n, m, 3 + s, cid) for s in range(B)])
+    p = np.tile([44.0, 44.0, 0.3 if cid == 1 else 0.0], (B, 1))
+    cons = ko.default_constraints(cid)
+    cmask = sum(1 << i for i in range(3) if cons[i])
+    Mo, po, status, nit, cost, cnt = E.newton_dense(cid, n, m, M, p, cmask, maxiter=2, tol=1e-10, chunk=1)
+    for b in range(B):
+        rm, rp, st = ko.newton_krylov(M[b], p[b], cid, method="lstsq", maxiter=2, tol=1e-10)
+        assert (int(status[b]), int(nit[b])) == (st["status"], st["nit"]), (b, status, nit, st)
+        assert abs(cost[b] - st["cost"]) <= 1e-8 * max(1.0, st["cost"]), (b, cost[b], st["cost"])
+        assert relerr(Mo[b], rm) < 1e-6 and np.allclose(po[b], rp, rtol=1e-7)
+    assert cnt[3] >= 1 and cnt[1] >= B
