@@ -67,6 +67,37 @@ size_t ks_workspace_bytes(int cls, int n, int m, int batch);
  * the device, one warp per seed.  seeds [B] uint32, params [B,3] (T, L, S), modes_out [B, Nm]. */
 int ks_populate_state(int cls, int n, int m, int batch, const uint32_t* seeds, const double* params, double* modes_out,
                       void* stream);
+/* The same with the reference's other modulation profiles (the `spatial_modulation`, `temporal_modulation`, `xshift`,
+ * `tscale`, `xscale`, `xvar`, `tvar` kwargs of _populate_state, ks/orbits.py:1772-1842).  `opt` is a HOST struct (NULL =
+ * defaults); NaN in a scale / variance field = the reference's default derived from (T, L). */
+enum { KS_SMOD_NONE = 0, KS_SMOD_GAUSSIAN, KS_SMOD_LAPLACE, KS_SMOD_LAPLACE_SQRT, KS_SMOD_PLATEAU_LINEAR,
+       KS_SMOD_EXPONENTIAL_LINEAR, KS_SMOD_FLAT_TOP };
+enum { KS_TMOD_NONE = 0, KS_TMOD_GAUSSIAN, KS_TMOD_LAPLACE, KS_TMOD_FLAT_TOP, KS_TMOD_LAPLACE_PLATEAU, KS_TMOD_TRUNCATE };
+enum { KS_XSHIFT_NONE = 0, KS_XSHIFT_SQRT, KS_XSHIFT_LOG, KS_XSHIFT_LIN };
+typedef struct KsPopulateOptions {
+  int spatial_modulation, temporal_modulation, xshift, reserved;
+  double tscale, xscale, xvar, tvar;
+} KsPopulateOptions;
+int ks_populate_state_ex(int cls, int n, int m, int batch, const uint32_t* seeds, const double* params,
+                         const KsPopulateOptions* opt, double* modes_out, void* stream);
+
+/* Orbit.resize for a batch (core.py:1167-1226 with OrbitKS._pad / _truncate, ks/orbits.py:1428-1564 and the SR / Anti
+ * overrides :3325-3394, :3735-3804): modes of an (n, m) grid -> modes of an (n_new, m_new) grid by zero padding /
+ * truncation of the time and space spectra, scaled by sqrt(n_new/n) then sqrt(m_new/m) as the reference does axis by
+ * axis.  in [B][(n-1) cols(m)], out [B][(n_new-1) cols(m_new)]. */
+int ks_resize_modes(int cls, int n, int m, int n_new, int m_new, int batch, const double* in, double* out, void* stream);
+
+/* Orbit.rescale (core.py:1831-1853) on FIELD arrays [B][n][m], in place: method 0 'inf' (max |u| -> magnitude),
+ * 1 'L1' (numpy.linalg.norm(field, ord=1) = largest column sum of |u|), 2 'L2' (Frobenius norm), 3 'LP'
+ * (sign(u) |u|^magnitude).  norms_out [B] (may be NULL) receives the norm that was divided out (0 for 'LP'). */
+int ks_rescale_field(int n, int m, int batch, double* field, double magnitude, int method, double* norms_out, void* stream);
+
+/* The norms OrbitKS.preprocess (ks/orbits.py:1566-1596; Relative :2969-3008) thresholds, from the modes (the transforms are
+ * orthogonal on the retained coefficients, so |u| = |modes| and |u_t| = |dt(modes)|): norms_out [B][2] = (|u|, |u_t|);
+ * code_out [B] = 1 if |u| is under the class's threshold (zero solution), 2 if |u_t| is (equilibrium), else 0; T == 0
+ * gives 2 (OrbitKS) / 1 (RelativeOrbitKS) as in the reference. */
+int ks_preprocess(int cls, int n, int m, int batch, const double* modes, const double* params, int32_t* code_out,
+                  double* norms_out, void* stream);
 
 /* OrbitKS.transform (ks/orbits.py:231-303) and the class-specific overrides: any basis -> any basis. */
 int ks_transform(int cls, int n, int m, int batch, int from_basis, int to_basis, const double* in, double* out,

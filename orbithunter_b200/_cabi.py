@@ -15,6 +15,10 @@ _SIG = {
     "ks_mode_size": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "ks_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ks_populate_state": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "ks_populate_state_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "ks_resize_modes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "ks_rescale_field": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_double, C.c_int, _P, _P]),
+    "ks_preprocess": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "ks_transform": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "ks_eqn": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "ks_matvec": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_uint32, _P, _P, C.c_size_t, _P]),
@@ -37,6 +41,17 @@ _SIG = {
                                   C.c_double, C.c_int, C.c_int, _P, _P, _P, C.POINTER(C.c_longlong), _P, C.c_size_t, _P]),
 }
 
+
+
+class KsPopulateOptions(C.Structure):
+    """include/ks_b200.h KsPopulateOptions (host struct)."""
+    _fields_ = [("spatial_modulation", C.c_int), ("temporal_modulation", C.c_int), ("xshift", C.c_int), ("reserved", C.c_int),
+                ("tscale", C.c_double), ("xscale", C.c_double), ("xvar", C.c_double), ("tvar", C.c_double)]
+
+
+SPATIAL_MODULATION_IDS = {"gaussian": 1, "laplace": 2, "laplace_sqrt": 3, "plateau_linear": 4, "exponential_linear": 5, "flat_top": 6}
+TEMPORAL_MODULATION_IDS = {"gaussian": 1, "laplace": 2, "flat_top": 3, "laplace_plateau": 4, "truncate": 5}
+XSHIFT_IDS = {"sqrt": 1, "log": 2, "lin": 3}
 EXPORTS = tuple(_SIG)
 
 

@@ -95,11 +95,21 @@ class BatchedOrbitKS:
         self.constraints = cons
 
     @classmethod
-    def from_seeds(cls, seeds, parameters, cls_name="OrbitKS", discretization=(32, 32), constraints=None, device=None):
+    def from_seeds(cls, seeds, parameters, cls_name="OrbitKS", discretization=(32, 32), constraints=None, device=None, **kwargs):
         """Random initial conditions generated ON THE DEVICE: the batch equivalent of the reference's
-        ``Cls(parameters=(T, L, S)).populate(attr="state", seed=s, discretization=(n, m))`` (ks/orbits.py:1738-1849,
-        default modulations) for every integer seed ``s`` in ``seeds`` (NumPy's legacy MT19937 / randn stream).
+        ``Cls(parameters=(T, L, S)).populate(attr="state", seed=s, discretization=(n, m), **kwargs)`` (ks/orbits.py:1738-1849)
+        for every integer seed ``s`` in ``seeds`` (NumPy's legacy MT19937 / randn stream).  ``kwargs``: the reference's
+        ``spatial_modulation``, ``temporal_modulation``, ``xshift`` (by name), ``tscale``, ``xscale``, ``xvar``, ``tvar``.
         ``parameters`` is (3,) or (B, 3).  RelativeOrbitKS: S is reset to 0 as the reference's populate does (:2872-2883)."""
+        from ._cabi import SPATIAL_MODULATION_IDS, TEMPORAL_MODULATION_IDS, XSHIFT_IDS, KsPopulateOptions
+
+        xs = kwargs.get("xshift", "sqrt")
+        if not isinstance(xs, str):
+            raise NotImplementedError("from_seeds: an array-valued xshift is only provided by the single-orbit populate()")
+        nan = float("nan")
+        opt = KsPopulateOptions(SPATIAL_MODULATION_IDS.get(kwargs.get("spatial_modulation", "laplace"), 0),
+                                TEMPORAL_MODULATION_IDS.get(kwargs.get("temporal_modulation", "gaussian"), 0), XSHIFT_IDS.get(xs, 0), 0,
+                                *(float(kwargs[k]) if kwargs.get(k) is not None else nan for k in ("tscale", "xscale", "xvar", "tvar")))
         if not torch.cuda.is_available():
             raise _lib.KsB200Error("orbithunter_b200 needs a CUDA device; there is no CPU path")
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -121,8 +131,10 @@ class BatchedOrbitKS:
         state = torch.empty((B,) + basis_shape(cid, n, m, "modes"), dtype=torch.float64, device=dev)
         if B:
             with torch.cuda.device(dev):
-                _lib.check(_lib.lib().ks_populate_state(cid, n, m, B, sd.data_ptr(), par.data_ptr(), state.data_ptr(),
-                                                        torch.cuda.current_stream().cuda_stream))
+                import ctypes
+
+                _lib.check(_lib.lib().ks_populate_state_ex(cid, n, m, B, sd.data_ptr(), par.data_ptr(), ctypes.addressof(opt),
+                                                           state.data_ptr(), torch.cuda.current_stream().cuda_stream))
         return cls(state, par, cid, "modes", (n, m), constraints)
 
     # ---- bookkeeping -------------------------------------------------------------------------------------------
@@ -267,6 +279,52 @@ class BatchedOrbitKS:
         if computation_basis not in ("modes", "spatial_modes"):
             raise ValueError(f"dx(computation_basis={computation_basis}); invalid basis for spectral differentiation. ")
         return self.transform(computation_basis)._deriv(1, order).transform(back)
+
+    def resize(self, *new_discretization):
+        """Orbit.resize for the batch (core.py:1167-1226; _pad / _truncate ks/orbits.py:1428-1564 and the SR / Anti overrides):
+        zero padding / truncation of the spatiotemporal modes on the device; comes back in the basis of self."""
+        new = new_discretization[0] if len(new_discretization) == 1 and not np.isscalar(new_discretization[0]) else new_discretization
+        n2, m2 = (int(x) for x in new)
+        if (n2, m2) == self.discretization:
+            return self
+        if n2 % 2 or m2 % 2:
+            raise ValueError("New discretization size must be an even number, preferably a power of 2")
+        src = self.transform("modes")
+        out = torch.empty((self.batch,) + basis_shape(self.cls_id, n2, m2, "modes"), dtype=torch.float64, device=self.state.device)
+        with torch.cuda.device(self.state.device):
+            _lib.check(_lib.lib().ks_resize_modes(self.cls_id, self.n, self.m, n2, m2, self.batch, _ptr(src.state), _ptr(out),
+                                                  torch.cuda.current_stream().cuda_stream))
+        res = self._like(out, basis="modes")
+        res.discretization = (n2, m2)
+        return res.transform(self.basis)
+
+    def rescale(self, magnitude, method="inf"):
+        """Orbit.rescale (core.py:1831-1853) for every orbit of the batch: field norm ('inf', 'L1', 'L2') set to ``magnitude``,
+        or the signed power ('LP'); result in the basis of self."""
+        mid = {"inf": 0, "L1": 1, "L2": 2, "LP": 3}.get(method)
+        if mid is None:
+            raise ValueError("Unrecognizable method.")
+        f = self.transform("field")
+        f = f._like(f.state.clone()) if f is self else f
+        with torch.cuda.device(self.state.device):
+            _lib.check(_lib.lib().ks_rescale_field(self.n, self.m, self.batch, _ptr(f.state), float(magnitude), mid, None,
+                                                   torch.cuda.current_stream().cuda_stream))
+        return f.transform(self.basis)
+
+    def preprocess_codes(self):
+        """Per-orbit classification of OrbitKS.preprocess (ks/orbits.py:1566-1596; Relative :2969-3008): (code, flip) with
+        code 0 = keep, 1 = zero solution, 2 = equilibrium (no temporal variation); flip (RelativeOrbitKS only): the orbit with
+        the shift negated has the smaller cost and is the one the reference carries on with."""
+        mo = self.transform("modes")
+        code = torch.empty(self.batch, dtype=torch.int32, device=self.state.device)
+        flip = torch.zeros(self.batch, dtype=torch.bool, device=self.state.device)
+        if self.cls_id == 1:
+            mirrored = mo._like(parameters=mo.parameters * torch.tensor([1.0, 1.0, -1.0], dtype=torch.float64, device=self.state.device))
+            flip = mo.cost() > mirrored.cost()
+        with torch.cuda.device(self.state.device):
+            _lib.check(_lib.lib().ks_preprocess(self.cls_id, self.n, self.m, self.batch, _ptr(mo.state), _ptr(mo.parameters),
+                                                _ptr(code), None, torch.cuda.current_stream().cuda_stream))
+        return code.cpu().numpy(), flip.cpu().numpy()
 
     def dot(self, other):
         return (self.state.reshape(self.batch, -1) * other.state.reshape(self.batch, -1)).sum(dim=1)

@@ -1,5 +1,5 @@
-// Random initial conditions on the device: OrbitKS._populate_state (orbithunter/ks/orbits.py:1738-1849, default
-// "laplace" spatial x "gaussian" temporal modulation) for a whole batch of integer seeds.
+// Random initial conditions on the device: OrbitKS._populate_state (orbithunter/ks/orbits.py:1738-1849, every spatial /
+// temporal modulation profile and xshift coupling the reference offers) for a whole batch of integer seeds.
 //
 // The reference draws randn(n-1, cols) from NumPy's legacy global generator after np.random.seed(seed): MT19937 seeded by
 // Knuth's recurrence (numpy/random/src/mt19937/mt19937.c mt19937_seed), 53-bit doubles from two 32-bit draws
@@ -11,6 +11,7 @@
 #pragma once
 #include <cstdint>
 
+#include "../../include/ks_b200.h"
 #include "ks_common.cuh"
 
 namespace kspop {
@@ -24,6 +25,10 @@ struct PopArgs {
   const double* params;   // [B][3]
   double* out;            // [B][rows*cols]
   int batch, n, m, cols;
+  // modulation profiles (ks/orbits.py:1797-1842); ids as in include/ks_b200.h; scale / variance overrides, NaN = the
+  // reference's default derived from (T, L)
+  int smod, tmod, xshift;
+  double tscale, xscale, xvar, tvar;
 };
 
 KS_DEVI uint32_t twist(uint32_t cur, uint32_t nxt, uint32_t far) {
@@ -57,6 +62,7 @@ KS_DEVI unsigned ballot(bool p, uint32_t*, int) { return __ballot_sync(0xfffffff
 KS_DEVI int popc(unsigned x) { return __popc(x); }
 KS_DEVI double add_rn(double a, double b) { return __dadd_rn(a, b); }
 #endif
+KS_DEVI bool ks_isnan(double v) { return v != v; }
 KS_DEVI double warp_sum(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 16);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -138,9 +144,10 @@ __global__ void __launch_bounds__(kWarps * 32) ks_populate_kernel(const PopArgs 
   const double norm0 = sqrt(warp_sum(ss));
   // modulation (ks/orbits.py:1797-1845) and renormalisation to the pre-modulation norm
   const double T = a.params[b * 3 + 0], L = a.params[b * 3 + 1];
-  const double tscale = rint(T / 20.0), xscale = rint(L / (ks::kTwoPi * ks::kSqrt2));
-  const double xvar = fmax(sqrt(xscale), 1.0), tvar = fmax(sqrt(tscale), 1.0);
-  const double sx = sqrt(xvar);
+  const double tscale = ks_isnan(a.tscale) ? rint(T / 20.0) : a.tscale;
+  const double xscale = ks_isnan(a.xscale) ? rint(L / (ks::kTwoPi * ks::kSqrt2)) : a.xscale;
+  const double xvar = ks_isnan(a.xvar) ? fmax(sqrt(xscale), 1.0) : a.xvar, tvar = ks_isnan(a.tvar) ? fmax(sqrt(tscale), 1.0) : a.tvar;
+  const double sx = sqrt(xvar), st = sqrt(tvar);
   const double fn = ks::kTwoPi * a.n / ks::kTwoPi, fm = ks::kTwoPi * a.m / ks::kTwoPi, rn = 1.0 / a.n, rm = 1.0 / a.m;
   double s2 = 0.0;
   for (int i = lane; i < nm; i += 32) {
@@ -150,8 +157,46 @@ __global__ void __launch_bounds__(kWarps * 32) ks_populate_kernel(const PopArgs 
     // entries land on kappa - 1.  Same expression, same rounding, here.
     const int ji = r <= h ? r : r - h, ki = (c < k ? c : c - k) + 1;
     const double j = floor(__dmul_rn(fn, __dmul_rn((double)ji, rn))), kap = floor(__dmul_rn(fm, __dmul_rn((double)ki, rm)));
-    double v = exp(-1.0 * fabs(kap - (xscale + sqrt(j))) / sx) * out[i];
-    v = exp(-((j - tscale) * (j - tscale)) / (2.0 * tvar)) * v;
+    // centre of the spatial profile, coupled to the time index (:1797-1805)
+    const double ctr = xscale + (a.xshift == KS_XSHIFT_SQRT ? sqrt(j) : a.xshift == KS_XSHIFT_LOG ? log(1.0 + j)
+                                 : a.xshift == KS_XSHIFT_LIN ? j : 0.0);
+    double ps = 1.0;
+    switch (a.smod) {
+      case KS_SMOD_GAUSSIAN: ps = exp(-((kap - ctr) * (kap - ctr)) / (2.0 * xvar)); break;
+      case KS_SMOD_LAPLACE: ps = exp(-1.0 * fabs(kap - ctr) / sx); break;
+      case KS_SMOD_LAPLACE_SQRT: ps = exp(-1.0 * sqrt(fabs(kap - ctr)) / sx); break;
+      case KS_SMOD_PLATEAU_LINEAR: {
+        const double q = ks::kTwoPi * kap / L, q2 = q * q;
+        ps = kap <= ctr ? 1.0 : 1.0 / (q2 - q2 * q2);
+        break;
+      }
+      case KS_SMOD_EXPONENTIAL_LINEAR: {
+        const double q = ks::kTwoPi * kap / L, q2 = q * q;
+        ps = exp(q2 - q2 * q2);
+        break;
+      }
+      case KS_SMOD_FLAT_TOP: {
+        const double z = fabs(kap - ctr) / xvar, z2 = z * z;
+        ps = exp(-(z2 * z2 * z));
+        break;
+      }
+      default: break;
+    }
+    double pt = 1.0;
+    switch (a.tmod) {
+      case KS_TMOD_GAUSSIAN: pt = exp(-((j - tscale) * (j - tscale)) / (2.0 * tvar)); break;
+      case KS_TMOD_LAPLACE: pt = exp(-1.0 * fabs(j - tscale) / st); break;
+      case KS_TMOD_FLAT_TOP: {
+        const double z = fabs(j - tscale) / tvar, z2 = z * z;
+        pt = exp(-(z2 * z2 * z));
+        break;
+      }
+      case KS_TMOD_LAPLACE_PLATEAU: pt = j < tscale ? 1.0 : exp(-1.0 * fabs(j - tscale) / st); break;
+      case KS_TMOD_TRUNCATE: pt = j > tscale ? 0.0 : 1.0; break;
+      default: break;
+    }
+    double v = ps * out[i];
+    v = pt * v;
     out[i] = v;
     s2 = fma(v, v, s2);
   }

@@ -1,123 +1,305 @@
-"""Gluing / tiling initial conditions from smaller orbits (reference orbithunter/gluing.py:16-302).
+"""Gluing / tiling of initial conditions, batched on the device (behaviour of reference orbithunter/gluing.py:16-421).
 
-``glue`` combines an array of orbits into one larger orbit by concatenating their fields (time along axis 0, space along
-axis 1) and averaging their dimensions; with ``strip_wise=True`` every strip is first re-proportioned by
-``aspect_ratio_correction`` (each orbit gets a share of the strip's grid points proportional to its period / length).
-``tile`` is the same with a symbol array and a dictionary of orbits.  The array bookkeeping is host-side NumPy as in the
-reference; the basis changes and rediscretisations run through the orbit classes (device transforms).  This is what builds
-the large-domain inputs (BASELINE config 4) that ``hunt`` then converges.
+A gluing is planned on the host as plain integer bookkeeping and executed on the GPU as a few batched operations:
+
+* every tile involved in a call -- and in ``glue_batch`` / ``tile_batch`` every tile of EVERY tiling of the call -- is a
+  "patch": a device field plus its class, (T, L) and current grid;
+* a gluing pass along one axis asks, per strip, for new patch sizes (``_apportion``: each orbit's share of the strip's grid
+  points follows its share of the strip's period / length, the reference's aspect-ratio correction, gluing.py:16-115) and
+  for the strip's dimensions (``_combined_dimensions``, Orbit.glue_dimensions core.py:899-945);
+* all resizes of a pass are grouped by (class, old grid, new grid) and run as ONE ``BatchedOrbitKS.resize`` per group
+  (forward transform, ``ks_resize_modes``, inverse transform); identical requests (the same tile appearing many times
+  in a symbol array, or in many tilings) are computed once;
+* the resized fields of a strip are joined with one device concatenation; the result is a patch of the next pass.
+
+``glue`` / ``tile`` / ``aspect_ratio_correction`` / ``rediscretize_tileset`` / ``generate_symbol_arrays`` keep the
+reference's names, arguments and results for single calls.
 """
 from __future__ import annotations
 
 import itertools
 
 import numpy as np
+import torch
 
-__all__ = ["aspect_ratio_correction", "glue", "tile", "rediscretize_tileset"]
+from .batch import BatchedOrbitKS
 
-
-def glue_dimensions(dimension_tuples, glue_shape, include_zero_dimensions=True):
-    """Orbit.glue_dimensions (core.py:899-945): per dimension, glue_shape[i] times the mean over the orbits."""
-    try:
-        arrays = [np.array(p) for p in dimension_tuples]
-        if include_zero_dimensions:
-            return tuple(glue_shape[i] * p.mean() for i, p in enumerate(arrays))
-        return tuple(glue_shape[i] * p[p > 0.0].mean() for i, p in enumerate(arrays))
-    except IndexError as ie:
-        raise ValueError("Gluing shape must have as many elements as the orbit type has dimensions") from ie
+__all__ = ["aspect_ratio_correction", "glue", "tile", "glue_batch", "tile_batch", "rediscretize_tileset", "generate_symbol_arrays"]
 
 
-def _object_array(orbits, shape=None):
-    arr = np.empty(len(orbits), dtype=object)
-    for i, o in enumerate(orbits):
-        arr[i] = o
-    return arr if shape is None else arr.reshape(shape)
+class _Patch:
+    """A field on the device with what the planner needs to know about it."""
+
+    __slots__ = ("cls", "field", "dims", "key")
+
+    def __init__(self, cls, field, dims, key=None):
+        self.cls, self.field, self.dims = cls, field, tuple(float(d) for d in dims)
+        self.key = key  # identity of the source orbit (for de-duplication); None for intermediate strips
+
+    @property
+    def shape(self):
+        return tuple(self.field.shape)
 
 
-def aspect_ratio_correction(orbit_array, axis=0, conserve_parity=True):
-    """gluing.py:16-115: resize a strip of orbits along ``axis`` in proportion to their dimensions along that axis."""
-    dims = np.array([o.dimensions()[axis] for o in orbit_array])
-    sizes = np.array([o.shapes()[0][axis] for o in orbit_array])
-    disc_total, dim_total = np.sum(sizes), np.sum(dims)
-    if dim_total == 0.0 or len(orbit_array.ravel()) == 1:
-        return orbit_array
-    new_sizes = np.zeros(len(orbit_array))
-    order = np.argsort(dims)
+def _as_patches(orbits):
+    """Host orbits -> patches in the field basis; orbits given in another basis are transformed in class/grid batches."""
+    out, pending = {}, {}
+    for o in orbits:
+        if id(o) in out:
+            continue
+        if o.basis == "field":
+            out[id(o)] = _Patch(type(o), torch.as_tensor(np.ascontiguousarray(o.state, dtype=np.float64)).cuda(), o.dimensions(), id(o))
+        else:
+            out[id(o)] = None
+            pending.setdefault((type(o), o.basis, tuple(o.discretization)), []).append(o)
+    for (cls, basis, disc), group in pending.items():
+        b = BatchedOrbitKS(np.stack([o.state for o in group]), np.array([[o.t, o.x, 0.0] for o in group]), cls._cls_name, basis, disc)
+        fields = b.transform("field").state
+        for i, o in enumerate(group):
+            out[id(o)] = _Patch(cls, fields[i], o.dimensions(), id(o))
+    return out
+
+
+def _apportion(sizes, dims, floors, conserve_parity=True):
+    """New grid sizes along one axis for the members of a strip (reference gluing.py:41-105).  The strip keeps its total
+    number of points.  Every member starts from its class minimum (raised by one if that would flip the parity of its
+    current size, when parity is conserved); the points left over are handed out in units of two (one, without parity) in
+    order of increasing dimension, each member taking the integer part of its proportional share of what is still
+    unassigned, and the member with the largest dimension takes the rest -- doubled, in both modes, as the reference does."""
+    sizes, dims = np.asarray(sizes, dtype=np.int64), np.asarray(dims, dtype=float)
+    base = np.asarray(floors, dtype=np.int64).copy()
+    unit = 1
     if conserve_parity:
-        min_sizes = np.array([ms + 1 if (ms % 2) != (sizes[i] % 2) else ms
-                              for i, ms in enumerate(o.minimal_shape()[axis] for o in orbit_array)])
-        disc_remainder = (disc_total - np.sum(min_sizes)) // 2
-        dim_remainder = dim_total
-        for idx in order[:-1]:
-            share = int(disc_remainder * (dims[idx] / dim_remainder))
-            new_sizes[idx] = min_sizes[idx] + 2 * share
-            dim_remainder -= dims[idx]
-            disc_remainder -= share
-        new_sizes[order[-1]] = min_sizes[order[-1]] + 2 * disc_remainder
-    else:
-        min_sizes = np.array([o.minimal_shape()[axis] for o in orbit_array])
-        disc_remainder = disc_total - np.sum(min_sizes)
-        dim_remainder = dim_total
-        for idx in order[:-1]:
-            share = int(disc_remainder * (dims[idx] / dim_remainder))
-            new_sizes[idx] = min_sizes[idx] + share
-            dim_remainder -= dims[idx]
-            disc_remainder -= share
-        new_sizes[order[-1]] = min_sizes[order[-1]] + 2 * disc_remainder  # (sic, gluing.py:103-105)
-    new_shapes = [tuple(int(new_sizes[j]) if i == axis else o.shapes()[0][i] for i in range(len(o.shape)))
-                  for j, o in enumerate(orbit_array)]
-    return _object_array([o.resize(shp) for o, shp in zip(orbit_array, new_shapes)])
+        base += (base % 2) != (sizes % 2)
+        unit = 2
+    spare = (int(sizes.sum()) - int(base.sum())) // unit
+    ranking = np.argsort(dims)
+    new = base.copy()
+    unassigned = float(dims.sum())
+    for member in ranking[:-1]:
+        take = int(spare * (dims[member] / unassigned))
+        new[member] += unit * take
+        spare -= take
+        unassigned -= dims[member]
+    new[ranking[-1]] += 2 * spare
+    return [int(v) for v in new]
+
+
+def _combined_dimensions(patches, counts, include_zero_dimensions=True):
+    """Orbit.glue_dimensions (core.py:899-945): per dimension, (number of tiles along it) x (mean over the tiles)."""
+    if len(counts) < len(patches[0].dims):
+        raise ValueError("Gluing shape must have as many elements as the orbit type has dimensions")
+    table = np.array([p.dims for p in patches])
+    out = []
+    for axis in range(table.shape[1]):
+        column = table[:, axis]
+        if not include_zero_dimensions:
+            column = column[column > 0.0]
+        out.append(counts[axis] * column.mean())
+    return tuple(out)
+
+
+def _resize_all(requests):
+    """requests: list of (patch, new_shape).  One batched device resize per (class, grid, new grid); duplicates once."""
+    done, groups = {}, {}
+    for patch, new_shape in requests:
+        if new_shape == patch.shape:
+            continue
+        ident = (patch.key if patch.key is not None else id(patch), new_shape)
+        if ident not in done:
+            done[ident] = None
+            groups.setdefault((patch.cls, patch.shape, new_shape), []).append((ident, patch))
+    for (cls, shape, new_shape), members in groups.items():
+        for a, (size, floor_) in enumerate(zip(new_shape, cls.minimal_shape())):
+            if size < floor_:
+                raise ValueError("minimum discretization requirements not met during resize.")
+        batch = BatchedOrbitKS(torch.stack([p.field for _, p in members]), torch.zeros(len(members), 3, dtype=torch.float64),
+                               cls._cls_name, "field", shape)
+        fields = batch.resize(new_shape).state
+        for i, (ident, _) in enumerate(members):
+            done[ident] = fields[i]
+    out = []
+    for patch, new_shape in requests:
+        if new_shape == patch.shape:
+            out.append(patch)
+        else:
+            ident = (patch.key if patch.key is not None else id(patch), new_shape)
+            out.append(_Patch(patch.cls, done[ident], patch.dims, None))
+    return out
+
+
+def _strips(grid_shape, axis):
+    """Index tuples selecting every strip of a layout along ``axis`` (the other indices fixed), in row-major order."""
+    others = [range(g) if i != axis else (slice(None),) for i, g in enumerate(grid_shape)]
+    return list(itertools.product(*others))
+
+
+def _glue_pass(layouts, axis, orbit_type, conserve_parity, include_zero_dimensions):
+    """One strip-wise pass along ``axis`` over MANY layouts at once (object arrays of patches): plan every strip, run all the
+    resizes of the pass together, concatenate.  Returns the collapsed layouts (extent 1 along ``axis``)."""
+    plans, requests = [], []
+    for li, layout in enumerate(layouts):
+        for sel in _strips(layout.shape, axis):
+            members = list(np.atleast_1d(layout[sel]).ravel())
+            counts = tuple(len(members) if a == axis else 1 for a in range(layout.ndim))
+            dims = _combined_dimensions(members, counts, include_zero_dimensions)
+            along = [p.dims[axis] for p in members]
+            if len(members) > 1 and sum(along) != 0.0:
+                sizes = _apportion([p.shape[axis] for p in members], along, [p.cls.minimal_shape()[axis] for p in members], conserve_parity)
+                targets = [tuple(s if a == axis else p.shape[a] for a in range(2)) for p, s in zip(members, sizes)]
+            else:
+                targets = [p.shape for p in members]
+            plans.append((li, sel, dims, len(requests), len(members)))
+            requests.extend(zip(members, targets))
+    resized = _resize_all(requests)
+    out = [np.empty(tuple(1 if a == axis else g for a, g in enumerate(layout.shape)), dtype=object) for layout in layouts]
+    for li, sel, dims, start, count in plans:
+        field = torch.cat([p.field for p in resized[start:start + count]], dim=axis)
+        out[li][tuple(0 if isinstance(s, slice) else s for s in sel)] = _Patch(orbit_type, field, dims, None)
+    return out
+
+
+def _run(layouts, orbit_type, strip_wise, kwargs):
+    """Glue every layout (object array of patches) of the call; returns one patch per layout."""
+    conserve_parity = kwargs.get("conserve_parity", True)
+    nzero = kwargs.get("include_zero_dimensions", True)
+    if strip_wise:
+        order = kwargs.get("gluing_order", None)
+        if order is None:
+            order = np.argsort(layouts[0].shape)
+        finished = [None] * len(layouts)
+        for axis in order:
+            layouts = _glue_pass(layouts, int(axis), orbit_type, conserve_parity, nzero)
+            for i, layout in enumerate(layouts):
+                if layout.size == 1:
+                    finished[i] = layout.ravel()[0]
+        if any(f is None for f in finished):
+            raise ValueError("strip-wise gluing did not produce a result; verify gluing_shape and gluing_order "
+                             "are not empty or disable the strip-wise correction.")
+        return finished
+    out = []
+    for layout in layouts:  # array-wise: every tile on the same grid, the dimensions averaged over the whole layout at once
+        members = list(layout.ravel())
+        dims = _combined_dimensions(members, layout.shape, nzero)
+        if len({p.shape for p in members}) != 1:
+            raise ValueError("array-wise gluing needs tiles of one discretization; use strip_wise=True or rediscretize_tileset")
+        rows = [torch.cat([p.field for p in layout[i, :]], dim=1) for i in range(layout.shape[0])]
+        out.append(_Patch(orbit_type, torch.cat(rows, dim=0), dims, None))
+    return out
+
+
+def _layout_of(orbit_array, patches):
+    arr = np.asarray(orbit_array, dtype=object)
+    if arr.ndim != 2:
+        raise ValueError("Gluing shape must have as many elements as the orbit type has dimensions")
+    layout = np.empty(arr.shape, dtype=object)
+    for idx in np.ndindex(arr.shape):
+        layout[idx] = patches[id(arr[idx])]
+    return layout
+
+
+def _ctor_kwargs(kwargs):
+    return {k: v for k, v in kwargs.items() if k not in ("basis", "gluing_order", "conserve_parity", "include_zero_dimensions")}
 
 
 def glue(orbit_array, orbit_type, strip_wise=False, **kwargs):
-    """gluing.py:118-272.  ``orbit_array``: NumPy object array of orbits (field basis) whose shape is the gluing layout."""
-    glue_shape = orbit_array.shape
-    tile_shape = orbit_array.ravel()[0].shapes()[0]
-    gluing_order = kwargs.get("gluing_order", np.argsort(glue_shape))
-    conserve_parity = kwargs.get("conserve_parity", True)
-    nzero = kwargs.get("include_zero_dimensions", True)
-    gluing_basis = kwargs.get("basis", orbit_type.bases_labels()[0])
-    ctor_kwargs = {k: v for k, v in kwargs.items() if k != "basis"}
-    if strip_wise:
-        glued_orbit = None
-        for gluing_axis in gluing_order:
-            slices = itertools.product(*(range(g) if i != gluing_axis else [slice(None)] for i, g in enumerate(glue_shape)))
-            strips = []
-            for gs in slices:
-                strip_shape = tuple(len(orbit_array[gs]) if n == gluing_axis else 1 for n in range(len(orbit_array.shape)))
-                zipped = tuple(zip(*(o.dimensions() for o in orbit_array[gs].ravel())))
-                strip_parameters = glue_dimensions(zipped, glue_shape=strip_shape, include_zero_dimensions=nzero)
-                corrected = aspect_ratio_correction(orbit_array[gs].ravel(), axis=gluing_axis, conserve_parity=conserve_parity)
-                state = np.concatenate(tuple(x.state for x in corrected), axis=gluing_axis)
-                strips.append(orbit_type(state=state, basis=gluing_basis, parameters=strip_parameters, **ctor_kwargs))
-            glue_shape = tuple(glue_shape[i] if i != gluing_axis else 1 for i in range(len(glue_shape)))
-            orbit_array = _object_array(strips, glue_shape)
-            if orbit_array.size == 1:
-                glued_orbit = orbit_array.ravel()[0]
-        if glued_orbit is None:
-            raise ValueError("strip-wise gluing did not produce a result; verify gluing_shape and gluing_order "
-                             "are not empty or disable the strip-wise correction.")
-        return glued_orbit
-    zipped = tuple(zip(*(o.dimensions() for o in orbit_array.ravel())))
-    glued_dimensions = glue_dimensions(zipped, glue_shape=glue_shape, include_zero_dimensions=nzero)
-    gluing_axis = len(glue_shape) - 1
-    fields = np.array([o.transform(to=orbit_type.bases_labels()[0]).state for o in orbit_array.ravel()])
-    state = fields.reshape(*orbit_array.shape, *tile_shape)
-    while len(state.shape) > len(tile_shape):
-        state = np.concatenate(state, axis=gluing_axis)
-    return orbit_type(state=state, basis=gluing_basis, parameters=glued_dimensions, **ctor_kwargs)
+    """Combine an array of orbits, laid out as they are to be joined (axis 0 = time, axis 1 = space), into one ``orbit_type``
+    instance (reference gluing.py:118-272): fields concatenated, dimensions = tiles-per-axis x mean tile dimension;
+    ``strip_wise`` first re-proportions every strip (see module docstring)."""
+    arr = np.asarray(orbit_array, dtype=object)
+    patches = _as_patches(arr.ravel())
+    result = _run([_layout_of(arr, patches)], orbit_type, strip_wise, kwargs)[0]
+    return orbit_type(state=result.field.cpu().numpy(), basis=kwargs.get("basis", orbit_type.bases_labels()[0]), parameters=result.dims,
+                      **_ctor_kwargs(kwargs))
 
 
 def tile(symbol_array, tiling_dictionary, orbit_type, **kwargs):
-    """gluing.py:275-302: glue the orbits that the symbols of ``symbol_array`` stand for."""
-    symbol_array = np.asarray(symbol_array)
-    orbits = _object_array([tiling_dictionary[s] for s in symbol_array.ravel()], symbol_array.shape)
+    """``glue`` for an array of dictionary keys (reference gluing.py:275-302)."""
+    symbols = np.asarray(symbol_array)
+    orbits = np.empty(symbols.shape, dtype=object)
+    for idx in np.ndindex(symbols.shape):
+        orbits[idx] = tiling_dictionary[symbols[idx].item() if hasattr(symbols[idx], "item") else symbols[idx]]
     return glue(orbits, orbit_type, **kwargs)
 
 
+def glue_batch(orbit_arrays, orbit_type, strip_wise=False, **kwargs):
+    """Many gluings in one go (the sweep over symbol arrays that the reference does one ``glue`` at a time): every layout of
+    ``orbit_arrays`` is glued with the same settings; tiles shared between layouts are uploaded and resized once, and every
+    pass runs its resizes as one batch per (class, grid, new grid).  Returns a list of BatchedOrbitKS (field basis), one per
+    distinct result grid, with ``.layout_index`` = positions of its members in ``orbit_arrays``."""
+    arrays = [np.asarray(a, dtype=object) for a in orbit_arrays]
+    patches = _as_patches([o for a in arrays for o in a.ravel()])
+    results = _run([_layout_of(a, patches) for a in arrays], orbit_type, strip_wise, kwargs)
+    by_shape = {}
+    for i, r in enumerate(results):
+        by_shape.setdefault(r.shape, []).append(i)
+    out = []
+    for shape, idx in by_shape.items():
+        params = torch.tensor([list(results[i].dims) + [0.0] for i in idx], dtype=torch.float64)
+        b = BatchedOrbitKS(torch.stack([results[i].field for i in idx]), params, orbit_type._cls_name, "field", shape)
+        b.layout_index = idx
+        out.append(b)
+    return out
+
+
+def tile_batch(symbol_arrays, tiling_dictionary, orbit_type, **kwargs):
+    """``glue_batch`` for a list of symbol arrays over one tiling dictionary."""
+    arrays = []
+    for sa in symbol_arrays:
+        sa = np.asarray(sa)
+        arr = np.empty(sa.shape, dtype=object)
+        for idx in np.ndindex(sa.shape):
+            arr[idx] = tiling_dictionary[sa[idx].item() if hasattr(sa[idx], "item") else sa[idx]]
+        arrays.append(arr)
+    return glue_batch(arrays, orbit_type, **kwargs)
+
+
+def aspect_ratio_correction(orbit_array, axis=0, conserve_parity=True):
+    """Resize a strip of orbits along ``axis`` in proportion to their dimensions along it (reference gluing.py:16-115); returns
+    an object array of resized orbits (the input itself for a single orbit or all-zero dimensions)."""
+    strip = np.asarray(orbit_array, dtype=object)
+    members = list(strip.ravel())
+    along = [o.dimensions()[axis] for o in members]
+    if sum(along) == 0.0 or len(members) == 1:
+        return orbit_array
+    sizes = _apportion([o.shapes()[0][axis] for o in members], along, [o.minimal_shape()[axis] for o in members], conserve_parity)
+    patches = _as_patches(members)
+    requests = [(patches[id(o)], tuple(s if a == axis else o.shapes()[0][a] for a in range(2))) for o, s in zip(members, sizes)]
+    out = np.empty(len(members), dtype=object)
+    for i, (o, p) in enumerate(zip(members, _resize_all(requests))):
+        out[i] = o._new(state=p.field.cpu().numpy(), basis="field", discretization=p.shape).transform(to=o.basis)
+    return out
+
+
 def rediscretize_tileset(tiling_dictionary, new_shape=None, **kwargs):
-    """gluing.py:355-421, explicit ``new_shape`` only: bring every tile to the same discretization (as non-strip-wise glue needs)."""
+    """Bring every tile of a dictionary to one grid (reference gluing.py:355-421): ``new_shape``, or the grid the class
+    conventions give the dictionary's average dimensions (``dimension_based_discretization`` of its most common class)."""
+    orbits = list(tiling_dictionary.values())
     if new_shape is None:
-        raise NotImplementedError("rediscretize_tileset needs an explicit new_shape here (the reference's default derives it "
-                                  "from dimension_based_discretization of the average dimensions)")
-    return {k: o.resize(*new_shape) for k, o in tiling_dictionary.items()}
+        mean_dims = tuple(float(np.mean(col)) for col in zip(*(o.dimensions() for o in orbits)))
+        classes = [type(o) for o in orbits]
+        commonest = max(set(classes), key=classes.count)
+        new_shape = commonest.dimension_based_discretization(mean_dims, **kwargs)
+    new_shape = tuple(int(v) for v in new_shape)
+    patches = _as_patches(orbits)
+    resized = _resize_all([(patches[id(o)], new_shape) for o in orbits])
+    return {k: o._new(state=p.field.cpu().numpy(), basis="field", discretization=new_shape).transform(to=o.basis)
+            for (k, o), p in zip(tiling_dictionary.items(), resized)}
+
+
+def generate_symbol_arrays(tiling_dictionary, glue_shape, unique=True):
+    """All symbol arrays of a shape over a dictionary's keys (reference gluing.py:305-352); with ``unique`` one representative
+    per class of arrays equal up to cyclic translation along the axes."""
+    keys, count = list(tiling_dictionary.keys()), int(np.prod(glue_shape))
+    arrays = (np.reshape(combo, glue_shape) for combo in itertools.product(keys, repeat=count))
+    if not unique:
+        return list(arrays)
+    seen, out = set(), []
+    shifts = list(itertools.product(*(range(g) for g in glue_shape)))
+    axes = tuple(range(len(glue_shape)))
+    for arr in arrays:
+        images = {tuple(np.roll(arr, s, axis=axes).ravel().tolist()) for s in shifts}
+        if seen.isdisjoint(images):
+            out.append(arr)
+        seen |= images
+    return out

@@ -376,8 +376,8 @@ class OrbitKS:
         new_shape = new_discretization
         if len(new_shape) == 1 and isinstance(new_shape[0], tuple):
             new_shape = tuple(new_shape[0])
-        if not new_shape:
-            raise NotImplementedError("resize() without an explicit shape (dimension_based_discretization) is not provided")
+        if not new_shape:  # core.py:1200-1203: the class conventions decide
+            new_shape = self.dimension_based_discretization(self.dimensions(), **kwargs)
         new_shape = tuple(int(x) for x in new_shape)
         out = self.copy().transform(to="modes")
         if tuple(self.discretization) != new_shape:
@@ -462,16 +462,58 @@ class OrbitKS:
             out.append(float(val))
         self.parameters = tuple(out)
 
+    # modulation profiles of the seed generator (ks/orbits.py:1797-1842): name -> f(index table, centre, variance, orbit)
+    _SPATIAL_MODULATIONS = {
+        "gaussian": lambda k, c, var, o: np.exp(-((k - c) ** 2) / (2 * var)),
+        "laplace": lambda k, c, var, o: np.exp(-1.0 * np.abs(k - c) / np.sqrt(var)),
+        "laplace_sqrt": lambda k, c, var, o: np.exp(-1.0 * np.sqrt(np.abs(k - c)) / np.sqrt(var)),
+        "flat_top": lambda k, c, var, o: np.exp(-((np.abs(k - c) / var) ** 5)),
+    }
+    _TEMPORAL_MODULATIONS = {
+        "gaussian": lambda j, c, var, o: np.exp(-((j - c) ** 2) / (2 * var)),
+        "laplace": lambda j, c, var, o: np.exp(-1.0 * np.abs(j - c) / np.sqrt(var)),
+        "flat_top": lambda j, c, var, o: np.exp(-((np.abs(j - c) / var) ** 5)),
+        "laplace_plateau": lambda j, c, var, o: np.where(j < c, 1.0, np.exp(-1.0 * np.abs(j - c) / np.sqrt(var))),
+        "truncate": lambda j, c, var, o: np.where(j > c, 0, 1),
+    }
+
+    @classmethod
+    def dimension_based_discretization(cls, dimensions, **kwargs):
+        """Grid size the reference's conventions assign to (T, L) (ks/orbits.py:1638-1694): powers of two near T/2 and
+        sqrt(2) L by default ('coarse' / 'fine' / 'power' variants), never below 32 (16 for 'coarse') nor the class minimum;
+        ``discretization=(N, None)`` pins an axis."""
+        resolution = kwargs.get("resolution", "default")
+        forced = kwargs.get("discretization", None) or (None, None)
+        # per axis: (exponent offset applied to log2 of the dimension, floor) for the power-of-two rules
+        rules = {"coarse": ((-2, 16), (-1, 16)), "fine": ((1, 32), (2, 32)), "default": ((-1, 32), (0.5, 32))}
+        out = []
+        for axis, (dim, pinned) in enumerate(zip(tuple(dimensions)[:2], forced)):
+            if pinned is not None:
+                out.append(pinned)
+                continue
+            if dim == 0:
+                size = cls._default_shape()[axis]
+            elif resolution == "power":
+                size = max(2 * (int(4 * dim ** 0.5) // 2), 32)
+            else:
+                shift, floor_ = rules.get(resolution, rules["default"])[axis]
+                size = max(2 ** int(np.log2(dim) + shift), floor_)
+            out.append(max(size, cls.minimal_shape()[axis]))
+        return tuple(out)
+
     def _populate_state(self, **kwargs):
+        """Random spatiotemporal Fourier modes (ks/orbits.py:1738-1849): legacy ``np.random.seed(seed); randn(rows, cols)``,
+        multiplied by a spatial profile centred on xscale (+ a time-dependent shift ``xshift``) and a temporal profile
+        centred on tscale, then renormalised to the norm the unmodulated draw had."""
         T, L = self.t, self.x
-        if kwargs.get("spatial_modulation", "laplace") != "laplace" or kwargs.get("temporal_modulation", "gaussian") != "gaussian":
-            raise NotImplementedError("only the reference's default modulations ('laplace' space, 'gaussian' time) are provided")
         tscale = kwargs.get("tscale", int(np.round(T / 20.0)))
         xscale = kwargs.get("xscale", int(np.round(L / (_TWO_PI * np.sqrt(2)))))
         xvar = kwargs.get("xvar", max([np.sqrt(xscale), 1]))
         tvar = kwargs.get("tvar", max([np.sqrt(tscale), 1]))
         np.random.seed(kwargs.get("seed", None))  # legacy global MT19937 stream, as in the reference
-        n, m = kwargs.get("discretization", None) or self.discretization or self._default_shape()
+        n, m = self.dimension_based_discretization(self.dimensions(), **kwargs)
+        if n < self.minimal_shape()[0] or m < self.minimal_shape()[1]:
+            warnings.warn("\nminimum discretization requirements not met; methods may not work as intended.", RuntimeWarning)
         self.discretization = (int(n), int(m))
         rows, cols = self.shapes()[2]
         # the reference truncates its floating-point frequency tables (spatial_frequencies(2 pi, m, 1), :1788-1791) with
@@ -482,11 +524,55 @@ class OrbitKS:
         time_ = np.concatenate(([0], jt, jt))[:, None]
         random_modes = np.random.randn(rows, cols)
         norm0 = np.linalg.norm(random_modes)
-        modes = np.exp(-1.0 * np.abs(space_ - (xscale + np.sqrt(time_))) / np.sqrt(xvar)) * random_modes
-        modes = np.exp(-((time_ - tscale) ** 2) / (2 * tvar)) * modes
+        xshift = kwargs.get("xshift", "sqrt")  # space-time coupling of the spatial centre (:1797-1805)
+        if isinstance(xshift, np.ndarray):
+            centre = xscale + xshift
+        else:
+            centre = xscale + {"sqrt": np.sqrt, "log": lambda j: np.log(1 + j), "lin": lambda j: j}.get(xshift, lambda j: 0 * j)(time_)
+        smod = kwargs.get("spatial_modulation", "laplace")
+        tmod = kwargs.get("temporal_modulation", "gaussian")
+        if smod in ("plateau_linear", "exponential_linear"):  # profiles of the linear KS spectrum q^2 - q^4 (:1816-1824)
+            q = _TWO_PI * space_ / L
+            with np.errstate(divide="ignore"):
+                growth = q ** 2 - q ** 4
+                prof = (np.divide(1, growth) if smod == "plateau_linear" else np.exp(growth)) * np.ones(time_.shape)
+            if smod == "plateau_linear":
+                prof[np.broadcast_to(space_ <= centre, prof.shape)] = 1
+        elif smod in self._SPATIAL_MODULATIONS:
+            prof = self._SPATIAL_MODULATIONS[smod](space_, centre, xvar, self)
+        else:
+            prof = np.ones(random_modes.shape)
+        modes = np.multiply(prof, random_modes)
+        tprof = self._TEMPORAL_MODULATIONS[tmod](time_, tscale, tvar, self) if tmod in self._TEMPORAL_MODULATIONS else np.ones(random_modes.shape)
+        modes = np.multiply(tprof, modes)
         self.state = (norm0 / np.linalg.norm(modes)) * modes
         self.basis = "modes"
 
+    def rescale(self, magnitude, method="inf"):
+        """Orbit.rescale (core.py:1831-1853): set the size of the FIELD -- max-norm ('inf'), 'L1' (induced matrix 1-norm as
+        numpy.linalg.norm(ord=1) gives for a 2-d array), 'L2' (Frobenius), or the signed power |u|^magnitude ('LP') --
+        and return in the basis of self.  The norm and the scaling run on the device (ks_rescale)."""
+        if method not in ("inf", "L1", "L2", "LP"):
+            raise ValueError("Unrecognizable method.")
+        out = self._batched().rescale(float(magnitude), method)
+        return self._new(state=self._host(out.state), basis=self.basis)
+
+    def preprocess(self):
+        """Equilibrium / zero-solution check of a converged orbit (ks/orbits.py:1566-1596; Relative :2969-3008).  The norms
+        of u and u_t are taken on the device (ks_preprocess).  The reference converts such orbits to its Equilibrium
+        classes, which are outside this package's scope: a vanishing field comes back as zeros of this class, a genuine
+        equilibrium is returned unchanged with ``.equilibrium = True``; everything else is ``self``."""
+        code, flip = self._batched().preprocess_codes()
+        code, flip = int(code[0]), bool(flip[0])
+        if code == 0:
+            if flip:  # RelativeOrbitKS: the mirrored shift has the smaller cost (:2974-2983)
+                return self._new(parameters=(self.t, self.x, -self.s))
+            return self
+        if code == 1:
+            return self._new(state=np.zeros(self.shapes()[0]), basis="field").transform(to=self.basis)
+        out = self.copy()
+        out.equilibrium = True
+        return out
 
 class RelativeOrbitKS(OrbitKS):
     _cls_name = "RelativeOrbitKS"

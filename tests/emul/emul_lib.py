@@ -179,3 +179,48 @@ def precondition(cls, n, m, state, gparams, params, cmask, pexp=(1.0, 4.0)):
     out, gp = np.zeros_like(state), np.zeros_like(gparams)
     _chk(L, L.ks_precondition(cls, n, m, state.shape[0], _p(state), _p(gparams), _p(params), cmask, pexp[0], pexp[1], _p(out), _p(gp), None))
     return out, gp
+
+
+def populate_ex(cls, n, m, seeds, params, spatial="laplace", temporal="gaussian", xshift="sqrt", tscale=None, xscale=None, xvar=None,
+                tvar=None):
+    import ctypes
+
+    L = lib()
+    spec = importlib.util.spec_from_file_location("_cabi", os.path.join(ROOT, "orbithunter_b200", "_cabi.py"))
+    cabi = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cabi)
+    nan = float("nan")
+    opt = cabi.KsPopulateOptions(cabi.SPATIAL_MODULATION_IDS.get(spatial, 0), cabi.TEMPORAL_MODULATION_IDS.get(temporal, 0),
+                                 cabi.XSHIFT_IDS.get(xshift, 0), 0, *(nan if v is None else float(v) for v in (tscale, xscale, xvar, tvar)))
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    params = np.ascontiguousarray(params, dtype=float)
+    out = np.zeros((len(seeds),) + mode_shape(cls, n, m))
+    _chk(L, L.ks_populate_state_ex(cls, n, m, len(seeds), _p(seeds), _p(params), ctypes.addressof(opt), _p(out), None))
+    return out
+
+
+def resize_modes(cls, n, m, n2, m2, modes):
+    L = lib()
+    modes = np.ascontiguousarray(modes, dtype=float)
+    out = np.zeros((modes.shape[0],) + mode_shape(cls, n2, m2))
+    _chk(L, L.ks_resize_modes(cls, n, m, n2, m2, modes.shape[0], _p(modes), _p(out), None))
+    return out
+
+
+def rescale_field(field, magnitude, method):
+    L = lib()
+    f = np.array(field, dtype=float, order="C")
+    norms = np.zeros(f.shape[0])
+    _chk(L, L.ks_rescale_field(f.shape[1], f.shape[2], f.shape[0], _p(f), float(magnitude), {"inf": 0, "L1": 1, "L2": 2, "LP": 3}[method],
+                               _p(norms), None))
+    return f, norms
+
+
+def preprocess(cls, n, m, modes, params):
+    L = lib()
+    modes = np.ascontiguousarray(modes, dtype=float)
+    params = np.ascontiguousarray(params, dtype=float)
+    code = np.zeros(modes.shape[0], dtype=np.int32)
+    norms = np.zeros((modes.shape[0], 2))
+    _chk(L, L.ks_preprocess(cls, n, m, modes.shape[0], _p(modes), _p(params), _p(code), _p(norms), None))
+    return code, norms

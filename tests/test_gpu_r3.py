@@ -1,0 +1,153 @@
+"""GPU (-m gpu): the auxiliary device operations through the product API against outputs of the unmodified reference
+(tests/golden/ks_aux_r3.npz): seed generation with every modulation, the tutorial's catalog seed (cost 8807.93719632008),
+rescale, resize, preprocess."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, relerr
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+CLASS_NAMES = ("OrbitKS", "RelativeOrbitKS", "ShiftReflectionOrbitKS", "AntisymmetricOrbitKS")
+
+
+@pytest.fixture(scope="module")
+def g3():
+    return np.load(os.path.join(GOLDEN, "ks_aux_r3.npz"))
+
+
+def test_from_seeds_with_every_modulation(g3):
+    from orbithunter_b200 import BatchedOrbitKS
+
+    n_checked = 0
+    for key in g3.files:
+        if not key.startswith("pop/") or key == "pop/override":
+            continue
+        _, tag, sm, tm, xs = key.split("/")
+        cid, shape = tag.split("_")
+        cid, (n, m) = int(cid), (int(v) for v in shape.split("x"))
+        b = BatchedOrbitKS.from_seeds([5 + cid, 5 + cid], (52.0, 41.0, 0.0), CLASS_NAMES[cid], (n, m), spatial_modulation=sm,
+                                      temporal_modulation=tm, xshift=xs)
+        got = b.cpu_state()
+        assert relerr(got[0], g3[key]) < 1e-12 and np.array_equal(got[0], got[1]), key
+        n_checked += 1
+    assert n_checked == 128
+    b = BatchedOrbitKS.from_seeds([9], (52.0, 41.0, 0.0), "OrbitKS", (32, 32), tscale=3, xscale=4, xvar=2.5, tvar=1.5,
+                                  spatial_modulation="gaussian", temporal_modulation="laplace")
+    assert relerr(b.cpu_state()[0], g3["pop/override"]) < 1e-12
+
+
+def test_catalog_seed_of_the_published_timing(g3):
+    """notebooks/tutorial.ipynb: OrbitKS().populate(seed=0, attr='all', discretization=(64, 64), spatial_modulation='gaussian',
+    temporal_modulation='truncate').rescale(5) -- the seed of numerical_method_benchmarks.csv (cost 8807.93719632008)."""
+    from orbithunter_b200 import BatchedOrbitKS, OrbitKS
+
+    np.random.seed(0)
+    o = OrbitKS().populate(seed=0, attr="all", discretization=(64, 64), spatial_modulation="gaussian",
+                           temporal_modulation="truncate").rescale(5)
+    assert o.basis == "modes" and np.allclose(o.parameters, g3["catalog/params"], rtol=1e-15)
+    assert relerr(o.state, g3["catalog/state"]) < 1e-13
+    assert abs(o.cost() - 8807.93719632008) < 1e-9 * 8807.93719632008 and abs(o.cost() - float(g3["catalog/cost"])) < 1e-8
+    # the same on the device generator
+    b = BatchedOrbitKS.from_seeds([0], tuple(g3["catalog/params"]), "OrbitKS", (64, 64), spatial_modulation="gaussian",
+                                  temporal_modulation="truncate").rescale(5.0)
+    assert relerr(b.cpu_state()[0], g3["catalog/state"]) < 1e-12
+    assert abs(float(b.cost()[0]) - 8807.93719632008) < 1e-8 * 8807.93719632008
+
+
+@pytest.mark.parametrize("cid", range(4))
+def test_rescale_resize_preprocess_on_device(g3, cid):
+    from orbithunter_b200 import BatchedOrbitKS
+    from orbithunter_b200.ks import CLASSES
+
+    C = CLASSES[CLASS_NAMES[cid]]
+    M = g3[f"rescale/{cid}/in"]
+    o = C(state=M, basis="modes", parameters=(44.0, 33.4, 0.0))
+    b = BatchedOrbitKS(np.stack([M, 0.5 * M]), np.tile([44.0, 33.4, 0.0], (2, 1)), CLASS_NAMES[cid])
+    for method, mag in (("inf", 5.0), ("L1", 7.0), ("L2", 3.0), ("LP", 1.5)):
+        ref = g3[f"rescale/{cid}/{method}"]
+        assert relerr(o.rescale(mag, method=method).state, ref) < 1e-13
+        got = b.rescale(mag, method).cpu_state()
+        assert relerr(got[0], ref) < 1e-13
+        if method != "LP":
+            assert relerr(got[1], ref) < 1e-13  # norm-based rescaling forgets the input's amplitude
+        f = o.transform(to="field").rescale(mag, method=method)
+        assert f.basis == "field" and relerr(f.state, g3[f"rescale/{cid}/{method}_field"]) < 1e-13
+    with pytest.raises(ValueError):
+        o.rescale(1.0, method="L7")
+    # resize: batched device kernel and the single-orbit class
+    M = g3[f"resize/{cid}/in"]
+    o = C(state=M, basis="modes", parameters=(44.0, 33.4, 0.0))
+    b = BatchedOrbitKS(M[None], [[44.0, 33.4, 0.0]], CLASS_NAMES[cid])
+    for (n2, m2) in ((48, 40), (16, 24), (32, 64), (24, 32), (64, 16)):
+        ref = g3[f"resize/{cid}/{n2}x{m2}"]
+        r = b.resize(n2, m2)
+        assert r.discretization == (n2, m2) and np.array_equal(r.cpu_state()[0], ref)
+        assert relerr(o.resize(n2, m2).state, ref) < 1e-15
+        rf = b.transform("field").resize((n2, m2))
+        assert rf.basis == "field" and relerr(rf.transform("modes").cpu_state()[0], ref) < 1e-13
+    big = C(state=g3[f"resize/{cid}/auto_in"], basis="modes", parameters=(150.0, 70.0, 0.0))
+    r = big.resize()
+    assert tuple(r.discretization) == tuple(int(v) for v in g3[f"resize/{cid}/auto_shape"]) and relerr(r.state, g3[f"resize/{cid}/auto"]) < 1e-15
+    # preprocess
+    for tag in ("generic", "tiny", "steady", "nearly_steady"):
+        key = f"prep/{cid}/{tag}"
+        o = C(state=g3[key + "/state"], basis="modes", parameters=tuple(g3[key + "/params"]))
+        res = o.preprocess()
+        kept = str(g3[key + "/result_class"]) == CLASS_NAMES[cid]
+        if kept:
+            assert not getattr(res, "equilibrium", False) and np.allclose(res.parameters, g3[key + "/result_params"])
+            assert np.array_equal(res.state, o.state)
+        elif tag == "tiny":
+            assert not res.state.any()
+        else:
+            assert res.equilibrium
+
+
+def test_batched_gluing_matches_reference():
+    """glue_batch / tile_batch: all golden layouts of tests/golden/ks_gluing.npz (outputs of the unmodified reference's glue and
+    tile) glued in ONE call -- shared tiles uploaded and resized once, one batched resize per (class, grid, new grid) and pass."""
+    from orbithunter_b200 import OrbitKS
+    from orbithunter_b200.gluing import aspect_ratio_correction, glue_batch, rediscretize_tileset, tile_batch
+
+    g = np.load(os.path.join(GOLDEN, "ks_gluing.npz"))
+    o = {t: OrbitKS(state=g[f"in/{t}/field"], basis="field", parameters=tuple(g[f"in/{t}/params"])) for t in "abc"}
+    a, b, c = o["a"], o["b"], o["c"]
+
+    def arr(rows):
+        x = np.empty((len(rows), len(rows[0])), dtype=object)
+        for i, r in enumerate(rows):
+            for j, v in enumerate(r):
+                x[i, j] = v
+        return x
+
+    strip_tags = ["time_strip", "mixed_strip"]
+    out = glue_batch([arr([[a], [b]]), arr([[a], [c]])], OrbitKS, strip_wise=True)
+    seen = 0
+    for batch in out:
+        fields, params = batch.cpu_state(), batch.cpu_parameters()
+        for row, li in enumerate(batch.layout_index):
+            tag = strip_tags[li]
+            assert batch.discretization == tuple(g[tag + "/shape"]) and np.allclose(params[row, :2], g[tag + "/params"][:2], rtol=1e-14)
+            assert relerr(fields[row], g[tag + "/field"]) < 1e-13, tag
+            seen += 1
+    assert seen == 2
+    plain = glue_batch([arr([[a], [b]]), arr([[b], [a]])], OrbitKS)
+    assert len(plain) == 1 and plain[0].batch == 2 and relerr(plain[0].cpu_state()[0], g["time/field"]) < 1e-13
+    assert np.array_equal(plain[0].cpu_state()[1], np.concatenate((b.state, a.state), axis=0))
+    tb = tile_batch([np.array([[0, 1], [1, 1]]), np.array([[0, 1], [1, 0]])], {0: a, 1: b}, OrbitKS, strip_wise=True)
+    got = {li: (bt, row) for bt in tb for row, li in enumerate(bt.layout_index)}
+    bt, row = got[0]
+    assert relerr(bt.cpu_state()[row], g["tile/field"]) < 1e-13 and np.allclose(bt.cpu_parameters()[row, :2], g["tile/params"][:2], rtol=1e-14)
+    bt, row = got[1]
+    assert relerr(bt.cpu_state()[row], g["grid_strip/field"]) < 1e-13
+    # the glued batch is a usable initial condition on the device path
+    assert float(bt.transform("modes").cost()[row]) > 0.0
+    # strip correction on its own, and the dictionary-wide default grid
+    fixed = aspect_ratio_correction(arr([[a], [c]])[:, 0], axis=0)
+    assert sum(f.discretization[0] for f in fixed) == 48 and all(f.basis == "field" for f in fixed)
+    same = rediscretize_tileset({0: a, 1: c})
+    assert {tuple(v.discretization) for v in same.values()} == {OrbitKS.dimension_based_discretization((35.0, 26.0))}
+    assert relerr(same[1].state, c.resize(same[1].discretization).state) < 1e-13
