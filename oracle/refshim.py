@@ -13,6 +13,11 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("ORBITHUNTER_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "orbithunter")):
+    # the GPU box has no /root/reference: use the unmodified copy oracle/build_ref.py made (oracle/_ref, git-ignored)
+    _carried = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    if os.path.isdir(os.path.join(_carried, "orbithunter")):
+        REFERENCE_ROOT = _carried
 
 
 def available():

@@ -73,3 +73,72 @@ def hunt_sweep(cls_name, n_seeds, T, L, discretization, methods="adj", chunk=409
         records.append(rec)
     local = torch.cat(records, dim=0) if records else torch.zeros((0, len(RECORD_FIELDS)), dtype=torch.float64, device=device)
     return gather_records(local)
+
+
+SWEEP_FIELDS = RECORD_FIELDS + ("code",)
+
+
+def two_stage_sweep(n_seeds, refine, T=44.0, L=33.4, cls_name="OrbitKS", discretization=(32, 32), first_seed=0, adj_maxiter=10000,
+                    adj_tol=1e-6, dense_maxiter=200, dense_tol=1e-10, dense_chunk=256, device=None):
+    """BASELINE configs[4]: the orbit-hunting sweep, strong-scaled over the initialised process group.
+
+    Every rank takes the contiguous shard of seeds [first_seed, first_seed + n_seeds) that ``shard_bounds`` gives it,
+    generates them on the device, runs ``hunt('adj')`` (stage 1) on all of them and ``hunt('lstsq')`` (stage 2, the dense
+    Newton step that actually converges orbits: configs[0]'s second method) on the first ``refine / world`` of its shard --
+    the adjoint end cost does not predict which seeds converge (profiles/r02m_sweep_statistics.json), so the refined subset is
+    a uniform sample -- classifies the refined orbits with ``preprocess`` (zero / equilibrium solutions) and gathers one
+    record per seed on rank 0.  No collective runs before the gather.
+
+    Returns (records, timings): records on rank 0 is an (n_seeds, 8) float64 tensor, columns SWEEP_FIELDS, ordered by seed
+    (code = -1 for seeds that were not refined); timings is a dict of this rank's stage wall times in seconds.
+    """
+    import time
+
+    from .batch import BatchedOrbitKS
+    from .optimize import hunt
+
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lo, hi = shard_bounds(n_seeds, rank, world)
+    rlo, rhi = shard_bounds(min(refine, n_seeds), rank, world)
+    n_ref = min(rhi - rlo, hi - lo)
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    tm = {}
+
+    def lap(key, t0):
+        torch.cuda.synchronize(device)
+        tm[key] = time.perf_counter() - t0
+        return time.perf_counter()
+
+    t = time.perf_counter()
+    seeds = np.arange(first_seed + lo, first_seed + hi)
+    batch = BatchedOrbitKS.from_seeds(seeds, (float(T), float(L), 0.0), cls_name, discretization, device=device)
+    t = lap("seed_generation_s", t)
+    r1 = hunt(batch, "adj", maxiter=adj_maxiter, tol=adj_tol)
+    t = lap("adjoint_s", t)
+    status, nit, cost = r1.status.to(torch.float64), r1.nit.to(torch.float64), r1.costs[-1].clone()
+    params = r1.orbit.parameters.clone()
+    code = torch.full((hi - lo,), -1.0, dtype=torch.float64, device=device)
+    tm["adjoint_steps"] = float(r1.nit.sum().item())
+    tm["dense_solves"] = 0.0
+    if n_ref > 0:
+        sub = r1.orbit._like(r1.orbit.state[:n_ref].contiguous(), r1.orbit.parameters[:n_ref].contiguous())
+        r2 = hunt(sub, "lstsq", maxiter=dense_maxiter, tol=dense_tol, chunk=dense_chunk)
+        t = lap("dense_newton_s", t)
+        codes, _ = r2.orbit.preprocess_codes()
+        status[:n_ref] = r2.status.to(torch.float64)
+        nit[:n_ref] += r2.nit.to(torch.float64)
+        cost[:n_ref] = r2.costs[-1]
+        params[:n_ref] = r2.orbit.parameters
+        code[:n_ref] = torch.as_tensor(codes, dtype=torch.float64, device=device)
+        tm["dense_solves"] = float(r2.dense_solves)
+        t = lap("preprocess_s", t)
+    else:
+        tm["dense_newton_s"] = tm["preprocess_s"] = 0.0
+    local = torch.stack([torch.as_tensor(seeds, dtype=torch.float64, device=device), status, nit, cost, params[:, 0], params[:, 1],
+                         params[:, 2], code], dim=1)
+    records = gather_records(local)
+    lap("gather_s", t)
+    tm["refined"] = float(n_ref)
+    tm["seeds"] = float(hi - lo)
+    return records, tm
