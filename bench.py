@@ -215,7 +215,7 @@ def sweep_block(args, rank, world, dev):
     rec, tm = two_stage_sweep(args.sweep_seeds, args.sweep_refine, dense_maxiter=args.sweep_dense_maxiter)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    keys = ("seed_generation_s", "adjoint_s", "dense_newton_s", "preprocess_s", "gather_s")
+    keys = ("seed_generation_s", "adjoint_s", "dense_newton_s", "preprocess_s", "rank_imbalance_s", "gather_s")
     sums = ("adjoint_steps", "dense_solves", "refined", "seeds")
     t = torch.tensor([wall] + [tm[k] for k in keys], dtype=torch.float64, device=dev)
     c = torch.tensor([tm[k] for k in sums], dtype=torch.float64, device=dev)

@@ -15,7 +15,7 @@ import torch
 from .batch import PARAMETER_LABELS, BatchedOrbitKS
 from .optimize import OrbitResult, hunt
 
-__all__ = ["continuation", "continuation_batch", "discretization_continuation"]
+__all__ = ["continuation", "continuation_batch", "discretization_continuation", "span_family"]
 
 
 def _equals_target(value, target):
@@ -145,3 +145,82 @@ def discretization_continuation(orbit_instance, target_discretization, cycle=Fal
             while result.status == 1 and not result.orbit.shapes()[0][ax] == target_discretization[ax]:
                 result = hunt(_increment_discretization(result.orbit, target_discretization[ax], step, axis=ax), **fresh())
     return result
+
+
+def span_family(orbit_instance, **kwargs):
+    """Drop-in for orbithunter.continuation.span_family (continuation.py:280-384): from a converged root orbit, walk every
+    dimension up and down in steps of ``step_sizes[dim]`` (default 0.01), re-converging each step, until a step fails or the
+    dimension leaves ``bounds[dim]``; returns [[root], branch of the first dimension, ...] with each branch ordered by
+    increasing dimension (root excluded), and stores every ``sampling_rate``-th member of every branch in the HDF5 file
+    ``filename`` (default 'family_' + root.filename()).
+
+    All walkers (two per dimension) advance in LOCK STEP: one batched ``hunt`` per step re-converges the next member of every
+    branch that is still alive, instead of the reference's one-orbit-at-a-time walk; a walker stops exactly where the
+    reference's loop does.  The members are written in one pass (``save=False`` skips the file).  Keyword arguments of
+    ``hunt`` pass through, as in the reference."""
+    from .h5io import _free_name, _insert, _open_tree, _orbit_attrs, write_tree
+
+    step_sizes = kwargs.get("step_sizes", {})
+    bounds = kwargs.get("bounds", {k: (0, np.inf) for k in orbit_instance.dimension_labels()})
+    filename = kwargs.get("filename", "".join(["family_", orbit_instance.filename()]))
+    skip = ("step_sizes", "bounds", "filename", "strides", "sampling_rate", "leafnames", "save", "step_size", "h5mode")
+    hunt_kwargs = {k: v for k, v in kwargs.items() if k not in skip}
+    root = orbit_instance.transform(to="modes")
+    labels = root.parameter_labels()
+    dims = [d for d in bounds if getattr(root, d) != 0.0]
+    # one walker per (dimension, direction): its current member, whether it still moves, the members it has collected
+    walkers = []
+    for d in dims:
+        for sign in (+1.0, -1.0):
+            walkers.append({"dim": d, "sign": sign, "step": abs(step_sizes.get(d, 0.01)), "orbit": root, "alive": True, "members": []})
+
+    def in_bounds(w):
+        v = getattr(w["orbit"], w["dim"])
+        return v < bounds.get(w["dim"])[1] if w["sign"] > 0 else v > bounds.get(w["dim"])[0]
+
+    while True:
+        moving = []
+        for w in walkers:
+            if not w["alive"]:
+                continue
+            if not in_bounds(w):  # the reference's while-condition: converged AND strictly inside the bounds
+                w["alive"] = False
+                continue
+            if getattr(w["orbit"], w["dim"]) != getattr(root, w["dim"]):
+                w["members"].append(w["orbit"])
+            moving.append(w)
+        if not moving:
+            break
+        # next member of every live branch: constrain its dimension, step it, re-converge -- batched per constraint set
+        groups = {}
+        for w in moving:
+            groups.setdefault(w["dim"], []).append(w)
+        for d, ws in groups.items():
+            col = labels.index(d)
+            states = np.stack([w["orbit"].state for w in ws])
+            params = np.array([[p + (w["sign"] * w["step"] if i == col else 0.0) for i, p in enumerate(w["orbit"].parameters)] for w in ws])
+            trial = BatchedOrbitKS(states, params, root._cls_name, "modes", root.discretization,
+                                   _constrained(root._default_constraints(), (d,)))
+            res = hunt(trial, **{k: (v.copy() if hasattr(v, "copy") else v) for k, v in hunt_kwargs.items()})
+            status = res.status.cpu().numpy()
+            for i, w in enumerate(ws):
+                if status[i] == 1:
+                    w["orbit"] = res.orbit[i]
+                else:
+                    w["alive"] = False
+    family = [[orbit_instance]]
+    tree = None
+    for d in dims:
+        up = [w for w in walkers if w["dim"] == d and w["sign"] > 0][0]["members"]
+        down = [w for w in walkers if w["dim"] == d and w["sign"] < 0][0]["members"]
+        branch = list(reversed(down)) + up
+        family.append(branch)
+        if kwargs.get("save", True) and branch:
+            if tree is None:
+                tree = _open_tree(filename, kwargs.get("h5mode", "a"))
+            for leaf in branch[:: int(kwargs.get("sampling_rate", 1))]:
+                name = leaf.filename(cls_name=False, extension="").lstrip("_") if kwargs.get("leafnames", False) else ""
+                _insert(tree, _free_name(tree, "", name), (leaf.state, _orbit_attrs(leaf, leaf.cost())))
+    if tree is not None:
+        write_tree(filename, tree)
+    return family

@@ -765,7 +765,21 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
             return fail(KS_ERR_LAUNCH, "dense Newton step: device error while checking the factorisation");
           if (n_redo == 0) break;
         }
-        if ((rc_dense = ksdh::dgemm_batched(s, false, true, nm, nm, N, 1.0, J, nm, sJ, J, nm, sJ, 0.0, G, nm, sG, C)) != 0) return rc_dense;
+        // G = J J^T is symmetric and only its lower triangle is read below: block rows x block columns up to the diagonal
+        // (a 4 x 4 partition does 10 of the 16 block products)
+        {
+          const int parts = nm >= 512 ? 4 : (nm >= 128 ? 2 : 1);
+          const int bs = (((nm + parts - 1) / parts) + ksd::kNb - 1) / ksd::kNb * ksd::kNb;  // multiple of the Cholesky block
+          for (int r0 = 0; r0 < nm; r0 += bs) {
+            const int mr = nm - r0 < bs ? nm - r0 : bs;
+            for (int c0g = 0; c0g <= r0; c0g += bs) {
+              const int mc = nm - c0g < bs ? nm - c0g : bs;
+              if ((rc_dense = ksdh::dgemm_batched(s, false, true, mr, mc, N, 1.0, J + r0, nm, sJ, J + c0g, nm, sJ, 0.0,
+                                                  G + r0 + (size_t)c0g * nm, nm, sG, C)) != 0)
+                return rc_dense;
+            }
+          }
+        }
         if (attempt == 0) KS_LAUNCH(ksd::diag_mean_kernel, C, ksd::kThreads, 0, s, (const double*)G, gmean, nm);
         else KS_LAUNCH(ksd::shift_diag_kernel, C, 256, 0, s, G, (const double*)lambda, nm);
         for (int blk = 0; blk < nblk; ++blk) {
@@ -776,9 +790,13 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
             if ((rc_dense = ksdh::dgemm_batched(s, false, true, rest, b, b, 1.0, G + k1 + (size_t)k0 * nm, nm, sG,
                                                 Li + (size_t)blk * ksd::kNb * ksd::kNb, ksd::kNb, sLi, 0.0, Lf + k1 + (size_t)k0 * nm, nm, sG, C)) != 0)
               return rc_dense;
-            if ((rc_dense = ksdh::dgemm_batched(s, false, true, rest, rest, b, -1.0, Lf + k1 + (size_t)k0 * nm, nm, sG,
-                                                Lf + k1 + (size_t)k0 * nm, nm, sG, 1.0, G + k1 + (size_t)k1 * nm, nm, sG, C)) != 0)
-              return rc_dense;
+            // lower triangle only, in column strips of 4 Cholesky blocks (each strip includes its diagonal square)
+            for (int c1s = k1; c1s < nm; c1s += 4 * ksd::kNb) {
+              const int wc = nm - c1s < 4 * ksd::kNb ? nm - c1s : 4 * ksd::kNb;
+              if ((rc_dense = ksdh::dgemm_batched(s, false, true, nm - c1s, wc, b, -1.0, Lf + c1s + (size_t)k0 * nm, nm, sG,
+                                                  Lf + c1s + (size_t)k0 * nm, nm, sG, 1.0, G + c1s + (size_t)c1s * nm, nm, sG, C)) != 0)
+                return rc_dense;
+            }
           }
         }
       }

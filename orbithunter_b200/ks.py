@@ -548,6 +548,23 @@ class OrbitKS:
         self.state = (norm0 / np.linalg.norm(modes)) * modes
         self.basis = "modes"
 
+    # ---- on-disk format (core.py:1855-2001, ks/orbits.py:1598-1636) -----------------------------------------------------
+    def filename(self, extension=".h5", decimals=3, cls_name=True):
+        """Conventional file name (core.py:1952-2001): class name + one '_<label><value with p for the point>' per non-zero
+        dimension, e.g. OrbitKS_t44p000_x33p400.h5."""
+        dims = "".join(f"_{lab}" + f"{d:.{decimals}f}".replace(".", "p") for lab, d in zip(self.dimension_labels(), self.dimensions())
+                       if d != 0 and d is not None)
+        if not cls_name and dims:
+            return (dims + extension).lstrip("_")
+        return (self.__class__.__name__ + dims + extension).lstrip("_")
+
+    def to_h5(self, filename=None, dataname=None, h5mode="a", verbose=False, include_cost=True, **kwargs):
+        """OrbitKS.to_h5 (ks/orbits.py:1598-1636: the cost is stored by default) through the package's own HDF5 writer."""
+        from .h5io import to_h5
+
+        return to_h5(self, filename=filename or "", groupname=kwargs.get("groupname", ""), dataname=dataname or "", h5mode=h5mode,
+                     verbose=verbose, include_cost=include_cost)
+
     def rescale(self, magnitude, method="inf"):
         """Orbit.rescale (core.py:1831-1853): set the size of the FIELD -- max-norm ('inf'), 'L1' (induced matrix 1-norm as
         numpy.linalg.norm(ord=1) gives for a 2-d array), 'L2' (Frobenius), or the signed power |u|^magnitude ('LP') --

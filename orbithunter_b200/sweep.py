@@ -137,6 +137,9 @@ def two_stage_sweep(n_seeds, refine, T=44.0, L=33.4, cls_name="OrbitKS", discret
         tm["dense_newton_s"] = tm["preprocess_s"] = 0.0
     local = torch.stack([torch.as_tensor(seeds, dtype=torch.float64, device=device), status, nit, cost, params[:, 0], params[:, 1],
                          params[:, 2], code], dim=1)
+    if world > 1:  # wait for the slowest rank here, so that gather_s is the collective alone
+        dist.barrier()
+    t = lap("rank_imbalance_s", t)
     records = gather_records(local)
     lap("gather_s", t)
     tm["refined"] = float(n_ref)

@@ -151,3 +151,50 @@ def test_batched_gluing_matches_reference():
     same = rediscretize_tileset({0: a, 1: c})
     assert {tuple(v.discretization) for v in same.values()} == {OrbitKS.dimension_based_discretization((35.0, 26.0))}
     assert relerr(same[1].state, c.resize(same[1].discretization).state) < 1e-13
+
+
+def test_span_family_and_hdf5_round_trip(tmp_path):
+    """span_family (continuation.py:280-384) against the unmodified reference's family of the polished rpo
+    (tests/golden/ks_family.npz): same branches, same members, same saved names; the file it writes is read back by read_h5;
+    to_h5 / to_h5_batch / read_h5 round trips with the reference's attribute set."""
+    from orbithunter_b200 import BatchedOrbitKS, RelativeOrbitKS
+    from orbithunter_b200.continuation import span_family
+    from orbithunter_b200.h5io import h5_tree, read_h5, to_h5_batch
+
+    g = np.load(os.path.join(GOLDEN, "ks_family.npz"))
+    gc = np.load(os.path.join(GOLDEN, "ks_continuation.npz"))
+    root = RelativeOrbitKS(state=gc["start/modes"], basis="modes", parameters=tuple(gc["start/params"]), discretization=(32, 32))
+    assert root.filename() == str(g["root_filename"])
+    fname = str(tmp_path / "family.h5")
+    fam = span_family(root, bounds={"t": tuple(g["bounds_t"]), "x": tuple(g["bounds_x"])}, step_sizes={"t": 0.01, "x": 0.01}, leafnames=True,
+                      filename=fname, methods="gmres", maxiter=40, tol=1e-6, scipy_kwargs={"restart": 50, "maxiter": 4, "rtol": 1e-8})
+    assert len(fam) == int(g["n_branches"]) and fam[0][0] is root
+    names = []
+    for b in range(1, len(fam)):
+        assert len(fam[b]) == int(g[f"branch{b}/size"]), b
+        for i, o in enumerate(fam[b]):
+            assert np.allclose(o.parameters, g[f"branch{b}/{i}/params"], rtol=1e-6)
+            assert relerr(o.state, g[f"branch{b}/{i}/modes"]) < 1e-5
+            assert o.filename(cls_name=False, extension="").lstrip("_") == str(g[f"branch{b}/{i}/leafname"])
+            names.append(str(g[f"branch{b}/{i}/leafname"]))
+    assert names == [str(s) for s in g["saved_names"]]
+    stored = h5_tree(fname)
+    assert sorted(stored) == sorted(names)
+    back = read_h5(fname, names[0])
+    assert isinstance(back, RelativeOrbitKS) and back.basis == "modes" and tuple(back.discretization) == (32, 32) and back.frame == "comoving"
+    assert np.array_equal(back.state, fam[1][0].state) and np.allclose(back.parameters, fam[1][0].parameters, rtol=0, atol=0)
+    assert stored[names[0]][1]["cost"] < 1e-6
+    # single-orbit to_h5 with the reference's collision rule, and the batch writer
+    f2 = str(tmp_path / "orbits.h5")
+    assert root.to_h5(filename=f2) == "0" and root.to_h5(filename=f2) == "1" and root.to_h5(filename=f2, dataname="rpo") == "rpo"
+    assert root.to_h5(filename=f2, dataname="rpo") == "rpo_0"
+    b = BatchedOrbitKS.from_seeds(np.arange(6), (44.0, 33.4, 0.0), "OrbitKS", (32, 32))
+    written = to_h5_batch(b, f2, groupname="sweep", select=[1, 3, 4])
+    assert written == ["sweep/0", "sweep/1", "sweep/2"]
+    group = read_h5(f2, "sweep")
+    assert len(group) == 3 and np.array_equal(group[1].state, b.cpu_state()[3])
+    costs = b.cost().cpu().numpy()
+    assert abs(h5_tree(f2)["sweep"]["2"][1]["cost"] - costs[4]) <= 1e-12 * costs[4]
+    everything = read_h5(f2)
+    assert len(everything) == 5  # '0', '1', 'rpo', 'rpo_0' and the 'sweep' group
+    assert read_h5(f2, "rpo", validate=True).parameters[:2] == root.parameters[:2]  # preprocess keeps a genuine orbit
