@@ -49,6 +49,11 @@ void ks_debug_warp32_pingpong(int on);
  * kernel (cross-check), 1 (default) = tile path with the CTA-resident fused kernel at 64x64, 2 = multi-pass tiles for
  * every shape; chunk_mb > 0 sets the workspace budget that bounds how many orbits one pass sequence covers. */
 void ks_debug_tile(int enabled, int chunk_mb);
+/* tuning / test hook, multi-pass tile path: 0 (default) = one CTA per tile, loads into registers; 1 = the row and column
+ * pass kernels are persistent and stage their tiles with the Tensor Memory Accelerator (cp.async.bulk.tensor boxes in and out,
+ * cp.async.bulk lines, two-stage shared-memory ring on mbarriers); 2 / 3 = TMA rows only / columns only.  Bit-identical
+ * results; measured slower (two resident CTAs per SM instead of three), see csrc/ks_tile_tma.cuh. */
+void ks_debug_tile_tma(int mode);
 /* tuning / test hook, 32x32 adjoint descent: passes every orbit runs inside one launch of the multi-pass kernel with its
  * state on chip (default 128); 0 = the one-pass-per-launch kernel with the state in global memory (cross-check). */
 void ks_debug_adjoint_inner(int passes);

@@ -67,6 +67,7 @@ int g_adj_inner = 128;  // 32x32 adjoint descent: passes per launch of the multi
 int g_gmres_cluster = 1;  // 0 = one CTA per orbit GMRES step (cross-check), 1 = auto cluster size, 2/4/8 = at least that size
 int g_tile_mode = 1;  // 0 = generic kernel, 1 = tile path with the CTA-resident 64x64 kernel, 2 = tile path, multi-pass only
 int g_tile_chunk_mb = 256;
+int g_tile_tma = 0;  // multi-pass tiles: 0 = plain pass kernels (default: faster, see ks_tile_tma.cuh), 1 = TMA-staged persistent rows and columns, 2 / 3 = rows / columns only
 bool use_tile(int n, int m) { return g_tile_mode != 0 && !g_force_generic && kst::size_ok(n) && kst::size_ok(m); }
 int tile_chunk(int n, int m, int cols, int batch) {
   const size_t per = kst::orbit_doubles(n, m, cols) * 8;
@@ -123,8 +124,11 @@ int dispatch(int cls, int n, int m, const KsEvalArgs& a, void* ws, size_t ws_byt
 }
 }  // namespace
 
+int ks_tile_tma_mode() { return g_tile_tma; }
+
 extern "C" {
 
+void ks_debug_tile_tma(int mode) { g_tile_tma = (mode >= 0 && mode <= 3) ? mode : 0; }
 int ks_b200_abi_version(void) { return 1; }
 const char* ks_last_error(void) { return g_err; }
 

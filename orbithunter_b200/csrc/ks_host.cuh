@@ -81,6 +81,8 @@ int ks_tile_run_c0(int op, int n, int m, int chunk, const KsEvalArgs& a, cudaStr
 int ks_tile_run_c1(int op, int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s);
 int ks_tile_run_c2(int op, int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s);
 int ks_tile_run_c3(int op, int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s);
+// ks_api.cu: 0 = plain pass kernels, 1 = TMA-staged rows and columns (ks_tile_tma.cuh), 2 = rows only, 3 = columns only
+int ks_tile_tma_mode();
 // 32x32 register-resident kernels, one translation unit per symmetry class (ks_w32_c{0..3}.cu); `variant` selects the
 // kernel build for eqn / costgrad (3, 4, 5: see ks_debug_warp32_variant)
 int ks_w32_run_c0(int op, int variant, const KsEvalArgs& a, cudaStream_t s);

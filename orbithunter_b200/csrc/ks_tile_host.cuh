@@ -6,6 +6,7 @@
 #include "ks_host.cuh"
 #include "ks_tile.cuh"
 #include "ks_tile64.cuh"
+#include "ks_tile_tma.cuh"
 
 #ifndef KS_TILE_CLS
 #error "define KS_TILE_CLS (0..3) before including ks_tile_host.cuh"
@@ -46,6 +47,80 @@ int tile_ensure_twiddles(cudaStream_t s) {
 #endif
   return 0;
 }
+#ifndef KS_HOST_EMUL
+// ---- TMA-staged persistent pass kernels (ks_tile_tma.cuh) ----
+typedef CUresult (*KsEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+KsEncodeTiledFn tile_encode_fn() {
+  static KsEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<KsEncodeTiledFn>(p);
+  }
+  return fn;
+}
+// XC[chunk][K][n] double2 as a 2-D float64 tensor: inner 2 n doubles (one line), outer chunk * K lines; box {2 TB, K}
+bool tile_xc_tensor_map(CUtensorMap* tm, double2* XC, int chunk, int K, int n, int TB) {
+  KsEncodeTiledFn enc = tile_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)2 * n, (cuuint64_t)chunk * K};
+  const cuuint64_t strides[1] = {(cuuint64_t)n * 16};
+  const cuuint32_t box[2] = {(cuuint32_t)2 * TB, (cuuint32_t)K};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, XC, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+template <class K>
+int tile_persistent_grid(K kern, size_t smem, int ntiles, DynSmemOptIn& optin) {
+  if (!optin.ensure(kern, (int)smem)) return -1;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kst::kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+  const int cap = nb * sm_count();
+  return ntiles < cap ? ntiles : cap;
+}
+template <int M, int MODE, int STAGES>
+int tile_row_tma_ms(const kst::TileArgs& ta, cudaStream_t s) {
+  using P = kstma::RowPlan<M, STAGES>;
+  auto kern = kstma::tile_row_tma_kernel<M, MODE, STAGES>;
+  static DynSmemOptIn optin;
+  const int grid = tile_persistent_grid(kern, P::bytes, ta.e.batch * ta.ntb, optin);
+  if (grid < 0) return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(row tma) failed");
+  CUtensorMap tm;
+  if (!tile_xc_tensor_map(&tm, ta.XC, ta.e.batch, P::K, ta.g.n, P::TB)) return fail(KS_ERR_LAUNCH, "cuTensorMapEncodeTiled failed");
+  KS_LAUNCH(kern, grid, kst::kThreads, P::bytes, s, ta, tm);
+  return 0;
+}
+template <int M, int MODE>
+int tile_row_tma_m(const kst::TileArgs& ta, cudaStream_t s) {
+  return tile_row_tma_ms<M, MODE, 2>(ta, s);
+}
+template <int MODE>
+int tile_row_tma(const kst::TileArgs& ta, cudaStream_t s) {
+  switch (ta.g.m) {
+    case 64: return tile_row_tma_m<64, MODE>(ta, s);
+    case 128: return tile_row_tma_m<128, MODE>(ta, s);
+    default: return tile_row_tma_m<256, MODE>(ta, s);
+  }
+}
+template <int CLS, int OP, int N, int STAGE, int STAGES>
+int tile_colfwd_tma_s(const kst::TileArgs& ta, cudaStream_t s) {
+  using P = kstma::ColPlan<N, STAGES>;
+  auto kern = kstma::tile_colfwd_tma_kernel<CLS, OP, N, STAGE, STAGES>;
+  static DynSmemOptIn optin;
+  const int grid = tile_persistent_grid(kern, P::bytes, ta.e.batch * ta.nkb, optin);
+  if (grid < 0) return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(col tma) failed");
+  KS_LAUNCH(kern, grid, kst::kThreads, P::bytes, s, ta);
+  return 0;
+}
+template <int CLS, int OP, int N, int STAGE>
+int tile_colfwd_tma(const kst::TileArgs& ta, cudaStream_t s) {
+  return tile_colfwd_tma_s<CLS, OP, N, STAGE, 2>(ta, s);
+}
+#endif
+
 template <int CLS, int N>
 int tile_colinv(const kst::TileArgs& ta, cudaStream_t s) {
   return tile_launch(kst::tile_colinv_kernel<CLS, N>, kst::tile_smem_bytes<N>(), ta.e.batch * ta.nkb, ta, s);
@@ -69,15 +144,36 @@ int tile_chunk_run(kst::TileArgs& ta, cudaStream_t s) {
   tile_colinv<CLS, N>(ta, s);
   ta.forward = nuu ? 1 : 0;
   ta.zero_nuu = nuu ? 0 : 1;
-  tile_row<kst::MODE_SQ>(ta, s);
-  tile_colfwd<CLS, OP, N, 1>(ta, s);
+#ifndef KS_HOST_EMUL
+  const int tma = ks_tile_tma_mode();
+  const bool tma_rows = tma == 1 || tma == 2, tma_cols = tma == 1 || tma == 3;
+#else
+  const bool tma_rows = false, tma_cols = false;
+#endif
+  int rc = 0;
+  auto row = [&](auto mode_c) {
+    constexpr int MODE = decltype(mode_c)::value;
+#ifndef KS_HOST_EMUL
+    if (tma_rows) return tile_row_tma<MODE>(ta, s);
+#endif
+    return tile_row<MODE>(ta, s);
+  };
+  auto col = [&](auto stage_c) {
+    constexpr int STAGE = decltype(stage_c)::value;
+#ifndef KS_HOST_EMUL
+    if (tma_cols) return tile_colfwd_tma<CLS, OP, N, STAGE>(ta, s);
+#endif
+    return tile_colfwd<CLS, OP, N, STAGE>(ta, s);
+  };
+  if ((rc = row(std::integral_constant<int, kst::MODE_SQ>{})) != 0) return rc;
+  if ((rc = col(std::integral_constant<int, 1>{})) != 0) return rc;
   if constexpr (OP == KS_OP_EQN) {
     KS_LAUNCH((kst::tile_finalize_kernel<CLS, OP>), (ta.e.batch + 127) / 128, 128, 0, s, ta);
   }
   if constexpr (OP != KS_OP_EQN) {
     ta.forward = 1;
-    tile_row<kst::MODE_MUL>(ta, s);
-    tile_colfwd<CLS, OP, N, 2>(ta, s);
+    if ((rc = row(std::integral_constant<int, kst::MODE_MUL>{})) != 0) return rc;
+    if ((rc = col(std::integral_constant<int, 2>{})) != 0) return rc;
   }
   return 0;
 }
@@ -131,11 +227,13 @@ int launch_tile(int n, int m, int chunk, const KsEvalArgs& a, cudaStream_t s) {
     if (e.out_cost) e.out_cost += b0;
     if (e.f_out) e.f_out += (size_t)b0 * g.nm;
     ta.e = e;
+    int rc = 0;
     switch (n) {
-      case 64: tile_chunk_run<CLS, OP, 64>(ta, s); break;
-      case 128: tile_chunk_run<CLS, OP, 128>(ta, s); break;
-      default: tile_chunk_run<CLS, OP, 256>(ta, s); break;
+      case 64: rc = tile_chunk_run<CLS, OP, 64>(ta, s); break;
+      case 128: rc = tile_chunk_run<CLS, OP, 128>(ta, s); break;
+      default: rc = tile_chunk_run<CLS, OP, 256>(ta, s); break;
     }
+    if (rc != 0) return rc;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "tile kernel launch failed");
 }

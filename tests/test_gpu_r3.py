@@ -198,3 +198,34 @@ def test_span_family_and_hdf5_round_trip(tmp_path):
     everything = read_h5(f2)
     assert len(everything) == 5  # '0', '1', 'rpo', 'rpo_0' and the 'sweep' group
     assert read_h5(f2, "rpo", validate=True).parameters[:2] == root.parameters[:2]  # preprocess keeps a genuine orbit
+
+
+@pytest.mark.parametrize("cid,shape,B", [(0, (256, 256), 5), (1, (128, 128), 9), (2, (64, 128), 7), (3, (128, 64), 7)])
+def test_tma_staged_tile_kernels_match_the_plain_ones(cid, shape, B):
+    """ks_tile_tma.cuh (cp.async.bulk.tensor boxes / cp.async.bulk lines, persistent CTAs, mbarrier ring) against the plain pass
+    kernels: the per-tile arithmetic is the same, so every op must agree bit for bit -- and with the oracle to 1e-12."""
+    from oracle import ks_oracle as ko
+    from orbithunter_b200 import BatchedOrbitKS, _lib
+
+    n, m = shape
+    L = _lib.lib()
+    u = BatchedOrbitKS.from_seeds(np.arange(B), (60.0, 44.0, 0.4 if cid == 1 else 0.0), CLASS_NAMES[cid], (n, m))
+    v = BatchedOrbitKS.from_seeds(np.arange(B) + 50, (60.0, 44.0, 0.0), CLASS_NAMES[cid], (n, m))
+    v.parameters[:, :] = 0.25
+    out = {}
+    try:
+        L.ks_debug_tile(2, 256)
+        for mode in (0, 1, 2, 3):
+            L.ks_debug_tile_tma(mode)
+            cost, grad = u.costgrad()
+            out[mode] = [t.cpu().numpy() for t in (cost, grad.state, grad.parameters, u.eqn().state, u.matvec(v).state, u.rmatvec(v).state,
+                                                    u.rmatvec(v).parameters, u.costgrad(preconditioning=True)[1].state)]
+    finally:
+        L.ks_debug_tile_tma(0)
+        L.ks_debug_tile(1, 256)
+    for mode in (1, 2, 3):
+        for a, b in zip(out[0], out[mode]):
+            assert np.array_equal(a, b), mode
+    M, p = u.cpu_state(), u.cpu_parameters()
+    oc, ogs, ogp, _ = ko.costgrad(M, p, cid)
+    assert relerr(out[1][1], ogs) < 1e-12 and relerr(out[1][0], oc) < 1e-12
