@@ -494,7 +494,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
       }
       hr[0] = hi[0] = 0.0;
       irfft32(ks::kSqrt2 * m1[0], hr, hi, x);
-      const double sw = h ? -q : q;
+      // everything between this store and the load of phase E is linear, so phase E's power-of-two normalisation 4 cP rides
+      // along here (exact: same bits as scaling there)
+      const double sw = (h ? -q : q) * (4.0 * cP);
       if (colact) {
 #pragma unroll
         for (int t = 0; t < 32; ++t) tile[(t * 15 + c) * 2 + (1 - h)] = sw * x[t];
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
     {
       double x[32];
 #pragma unroll
-      for (int t = 0; t < 32; ++t) x[t] = (4.0 * cP) * tile[(t * 15 + cc) * 2 + h];
+      for (int t = 0; t < 32; ++t) x[t] = tile[(t * 15 + cc) * 2 + h];
       double p0, pr[16], pi[16];
       rfft32_fwd(x, p0, pr, pi);
       pr[0] = (0.5 * ks::kSqrt2) * p0;

@@ -228,4 +228,5 @@ def test_tma_staged_tile_kernels_match_the_plain_ones(cid, shape, B):
             assert np.array_equal(a, b), mode
     M, p = u.cpu_state(), u.cpu_parameters()
     oc, ogs, ogp, _ = ko.costgrad(M, p, cid)
-    assert relerr(out[1][1], ogs) < 1e-12 and relerr(out[1][0], oc) < 1e-12
+    tol = max(1e-12, 64 * 2.2e-16 * (2 * np.pi * (m // 2 - 1) / 44.0) ** 4)  # the adjoint amplifies FFT round-off by q_max^4
+    assert relerr(out[1][1], ogs) < tol and relerr(out[1][0], oc) < 1e-12
