@@ -36,8 +36,8 @@ def build(force=False, verbose=False):
     objs, procs = [], []
     for src in sources():  # one nvcc per translation unit, all at once
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-diag-suppress", "128,177", "-Xcompiler", "-fPIC", "-I", CSRC, "-I", INCLUDE, "-c", src,
-               "-o", obj]
+        cmd = [NVCC, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-diag-suppress", "128,177", "-Xcompiler", "-fPIC", "-I", CSRC, "-I", INCLUDE,
+               *os.environ.get("KS_NVCC_FLAGS", "").split(), "-c", src, "-o", obj]  # KS_NVCC_FLAGS: tuning builds (-DKS_...)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd)))

@@ -15,6 +15,7 @@
 //                exchanged except for RelativeOrbitKS' shift terms (warp shuffles).
 // Scalings are those of ks_warp32.cuh: field arrays hold 64 u, forward outputs are doubled, constants cN, cP.
 #pragma once
+#include "ks_fft32_gen.cuh"
 #include "ks_warp32.cuh"
 
 namespace ksx1 {
@@ -33,6 +34,9 @@ KS_HD constexpr int smem_bytes(bool adj) { return kWarpsPerCta * warp_smem_doubl
 // ks_warp32.cuh's convention has the k >= 1 outputs doubled; here that factor (x2 per forward transform, x4 for the two
 // dimensions) is folded into the scale constants applied at the tile loads of the COL phases.
 KS_DEVI void rfft32_fwd(const double (&x)[32], double& c0, double (&cr)[16], double (&ci)[16]) {
+#ifndef KS_X1_PACKED_IRFFT
+  ksg32::rfft32(x, c0, cr, ci);  // generated decimation in time, 163 instructions (tools/gen_fft32.py)
+#else
   double yr[17], yi[17];
   ksfft::rfft_dit<32, 1, 0, 32>(x, yr, yi);
   c0 = yr[0];
@@ -42,10 +46,16 @@ KS_DEVI void rfft32_fwd(const double (&x)[32], double& c0, double (&cr)[16], dou
     ci[k] = yi[k];
   }
   cr[0] = ci[0] = 0.0;
+#endif
 }
 
 // h0 real, (hr, hi)[k], k = 1..15 -> x[n] = h0 + sum_k 2 Re(H[k] e^{+2 pi i k n / 32})     (Nyquist term zero)
+// Generated decimation-in-frequency transform with deferred twiddle scales (tools/gen_fft32.py): 162 fp64 instructions.
+// -DKS_X1_PACKED_IRFFT selects the earlier route through a packed complex length-16 FFT (233 instructions; cross-check).
 KS_DEVI void irfft32(double h0, const double (&hr)[16], const double (&hi)[16], double (&x)[32]) {
+#ifndef KS_X1_PACKED_IRFFT
+  ksg32::irfft32(h0, hr, hi, x);
+#else
   double gr[16], gi[16];
   gr[0] = h0;
   gi[0] = h0;
@@ -68,6 +78,7 @@ KS_DEVI void irfft32(double h0, const double (&hr)[16], const double (&hi)[16], 
     x[2 * m] = gr[m];
     x[2 * m + 1] = gi[m];
   }
+#endif
 }
 
 // Packed lane-major layout of the fused adjoint pass' internal orbit / gradient buffers: per orbit 16 pairs x 32 lanes of
