@@ -52,41 +52,90 @@ def make_seeds(first, count):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons while the GPU is under the benchmark's load, through NVML (no subprocess: forking
+    nvidia-smi from the benchmark process measurably disturbed the 0.5 ms timed region -- 0.69 instead of 0.54 ms on the
+    ranks it hit, profiles/r02u_n8_clock_sampler_effect.json).  The first sample is taken `delay` seconds after the start, so
+    the sub-millisecond timed region itself is never touched; the same launches are then repeated (untimed) for a second so
+    that the samples are taken under exactly that load.  Falls back to nvidia-smi when pynvml is missing."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+    def __init__(self, index, delay=0.05):
+        self.index, self.samples, self.reasons, self.max_mhz, self.delay = index, [], set(), None, delay
+        self.disabled = False
         self._stop = threading.Event()
         self._th = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+        except Exception:
+            self._nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except (ValueError, IndexError):
+                pass
+        return index
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)))
+        self.max_mhz = float(n.nvmlDeviceGetMaxClockInfo(self._handle, n.NVML_CLOCK_SM))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+        for nm, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if mask & bit:
+                self.reasons.add(nm)
+
+    def _sample_smi(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        self.samples.append(float(f[0]))
+        self.max_mhz = float(f[1])
+        for nm, val in zip(names, f[2:]):
+            if val.lower().startswith("active"):
+                self.reasons.add(nm)
 
     def _run(self):
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        if self._stop.wait(self.delay):
+            return
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for nm, val in zip(names, f[2:]):
-                    if val.lower().startswith("active"):
-                        self.reasons.add(nm)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
-        self._th.start()
+        if not self.disabled:
+            self._th.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._th.join(timeout=6)
+        if not self.disabled:
+            self._th.join(timeout=6)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml" if self._nvml is not None else "nvidia-smi",
+                "note": "sampled every 50 ms from 50 ms after the start of the timed region on, while the timed launches are repeated "
+                        "(the timed region itself lasts well under a millisecond)"}
 
 
 def cpu_port_evals_per_s(modes, params, budget_s, procs):
@@ -386,7 +435,8 @@ def main():
     ap.add_argument("--no-side", action="store_true", help="skip the side blocks (sweep, config2, config3, other shapes)")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--sweep-seeds", type=int, default=65536)
-    ap.add_argument("--sweep-refine", type=int, default=2048, help="seeds (over all ranks) that also get the dense second stage")
+    ap.add_argument("--sweep-refine", type=int, default=4096, help="seeds (over all ranks) that also get the dense second stage")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="debug: do not poll nvidia-smi during the timed region")
     ap.add_argument("--sweep-dense-maxiter", type=int, default=200)
     ap.add_argument("--hunt-maxiter", type=int, default=10000)
     ap.add_argument("--variant", type=int, default=None, help="tuning: warp32 kernel variant (ks_debug_warp32_variant)")
@@ -453,7 +503,9 @@ def main():
             side.synchronize()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    sampler = ClockSampler(local_rank)
+    sampler.disabled = args.no_clock_sampler
+    with sampler as clocks:
         with torch.cuda.stream(side):
             ev0.record()
             if graph is not None:
@@ -543,7 +595,11 @@ def main():
                         "as here (tests/golden/ks_cfg0_table.npz) -- converged orbits/s is the sweep block's number",
             }
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [ms]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [float(x[0]) for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
     checksum = float(sets[0]["cost"].sum().item())
@@ -590,6 +646,7 @@ def main():
                 "d2h_bytes_per_step": BATCH * (NM + 3 + 1) * 8, "steps": e2e_steps},
         "gpu_launches": args.steps, "clocks": clocks.summary(), "checksum_cost_sum": checksum,
         "single_launch_ms": {"best": single[0], "median": single[len(single) // 2], "n": len(single)},
+        "timed_region_ms_per_rank": per_rank_ms,
     }
     if hunt_stats is not None:
         line["adjoint_descent"] = hunt_stats
