@@ -27,7 +27,16 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kTileDoubles = 32 * 15 * 2;  // XB tile of one orbit: 480 double2
 constexpr int kPackedDoubles = 16 * 32 * 2;  // per orbit, packed lane-major layout of the fused adjoint pass (below)
 constexpr int kStageDoubles = 31 * 32;      // cp.async landing zone for the next orbit's half tuples (lane-private slots)
-KS_HD constexpr int warp_smem_doubles(bool adj) { return kTileDoubles + (adj ? 2 * kPackedDoubles : kStageDoubles); }  // adj: u and g, packed
+// -DKS_X1_PARK: u's and F's half tuples wait in shared memory while the row phases run (below) instead of in 62 registers.
+// Measured (profiles/r02w_x1_register_parking.jsonl): no gain -- 26.0 vs 25.0 us per 4096-orbit launch, 337 vs 334 us per
+// 65 536 -- ptxas still takes all 255 registers and the dependent-issue stalls stay; off by default.
+#ifdef KS_X1_PARK
+constexpr bool kPark = true;
+#else
+constexpr bool kPark = false;
+#endif
+// adj: u and g, packed; otherwise the landing zone and (kPark) a second lane-private area of the same size
+KS_HD constexpr int warp_smem_doubles(bool adj) { return kTileDoubles + (adj ? 2 * kPackedDoubles : (kPark ? 2 : 1) * kStageDoubles); }
 KS_HD constexpr int smem_bytes(bool adj) { return kWarpsPerCta * warp_smem_doubles(adj) * 8; }
 
 // x[32] real -> c0 = DFT32(x)[0], (cr, ci)[k] = DFT32(x)[k], k = 1..15   (forward sign e^{-i...}, unnormalised).
@@ -123,6 +132,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
   double* tile = smem + warp * kWarpSmemDoubles;  // tile[(t * 15 + c) * 2 + component]
   double* stage = tile + kTileDoubles + lane;     // slot s of this lane at stage[s * 32]
   double* pstage = tile + kTileDoubles + lane * 2;  // packed variant (fused adjoint pass): pair pr at pstage[pr * 64]
+  // PARK (eqn / costgrad): the row phases B and D are the register-hungry ones (field row + product + FFT working set), and
+  // the 31 half tuples of u (needed again in stage 1) resp. F (needed again in stage 2) used to sit in 62 registers right
+  // through them.  Now u is re-read from the landing zone in phase C -- the next orbit's prefetch is issued only then, which
+  // still leaves it half an orbit to land -- and F waits in a second lane-private area until phase E.
+  constexpr bool PARK = kPark && !(OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI);
+  double* park = tile + kTileDoubles + kStageDoubles + lane;  // slot s of this lane at park[s * 32]
   const int c = lane >> 1, h = lane & 1;
   const bool colact = c < 15;
   const int cc = colact ? c : 14;
@@ -335,7 +350,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
         }
       }
     }
-    if constexpr (!ADJM) prefetch(orbit + nw, next);
+    if constexpr (!ADJM && !PARK) prefetch(orbit + nw, next);
     {
       double x[32];
       double hr[16], hi[16];
@@ -386,6 +401,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
       rfft32_fwd(x, n0, nr, ni);
       nr[0] = (0.5 * ks::kSqrt2) * n0;
       ni[0] = 0.0;
+      if constexpr (PARK) {  // u's half tuples again (they left the registers after phase A), then release the landing zone
+        static_for<0, 16>([&](auto Jc) {
+          constexpr int J = decltype(Jc)::value;
+          const bool pres = (J & 1) ? presO : presE;
+          m1[J] = pres ? stage[(J == 0 ? 0 : 2 * J - 1) * 32] : 0.0;
+          if constexpr (J > 0) m2[J] = pres ? stage[(2 * J) * 32] : 0.0; else m2[J] = 0.0;
+        });
+        prefetch(orbit + nw, next);
+      }
       static_for<0, 16>([&](auto Jc) {
         constexpr int J = decltype(Jc)::value;
         const bool pres = (J & 1) ? presO : presE;
@@ -495,6 +519,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
         }
       }
       if constexpr (OP == KS_OP_EQN) continue;
+      if constexpr (PARK) {
+#pragma unroll
+        for (int J = 0; J < 16; ++J) {
+          park[(J == 0 ? 0 : 2 * J - 1) * 32] = m1[J];
+          if (J > 0) park[(2 * J) * 32] = m2[J];
+        }
+      }
       // second inverse: spectrum of F's half -> its field component; Dx F = iq (A_F + i B_F): h0 writes q A_F to .y,
       // h1 writes -q B_F to .x
       double hr[16], hi[16];
@@ -551,7 +582,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const
         constexpr int J = decltype(Jc)::value;
         const bool pres = (J & 1) ? presO : presE;
         const double w = (J == 0) ? 0.0 : wbase * (J * (1.0 / 32.0));
-        const double f1 = m1[J], f2 = m2[J];
+        double f1, f2;
+        if constexpr (PARK) {  // F's half tuples back from their lane-private slots (written by this lane in phase C)
+          f1 = park[(J == 0 ? 0 : 2 * J - 1) * 32];
+          f2 = (J == 0) ? 0.0 : park[(2 * J) * 32];
+        } else {
+          f1 = m1[J];
+          f2 = m2[J];
+        }
         double g1 = fma(d, f1, fma(w, f2, -pr[J]));
         double g2 = (J == 0) ? 0.0 : fma(d, f2, fma(-w, f1, -pi[J]));
         if constexpr (REL) {  // + (S/T) dx(F)

@@ -27,6 +27,16 @@ def newton_krylov(orb: BatchedOrbitKS, method="gmres", tol=1e-6, ftol=1e-9, maxi
     tol, ftol, maxiter, min_step, preconditioning = (_pop(v) for v in (tol, ftol, maxiter, min_step, preconditioning))
     if not kwargs.get("backtracking", True):
         min_step = 1
+    if maxiter is None or int(maxiter) <= 0:
+        # the reference's loops only stop at nit == maxiter (optimize.py:2183), so maxiter <= 0 never terminates there
+        raise ValueError("maxiter must be a positive integer")
+    if method != "lstsq" and kwargs.get("step_size", 1) != 1:
+        # the reference's Newton-type loops restart every outer iteration at step_size (optimize.py:756, :1315); the device
+        # line search starts at the full step
+        raise NotImplementedError(f"hunt('{method}', step_size != 1) is not provided on the device path")
+    if method == "newton_descent" and (preconditioning or kwargs.get("approximation", False)):
+        # optimize.py:757-815 right-preconditions the pseudo-inverse step / runs the approximate-inverse inner loop
+        raise NotImplementedError("hunt('newton_descent') with preconditioning=True or approximation=True is not provided")
     sk = dict(scipy_kwargs or {})
     orb._need_modes()
     out = orb.copy()

@@ -74,6 +74,8 @@ def _adjoint_descent(orb: BatchedOrbitKS, tol=1e-6, ftol=1e-9, maxiter=10000, mi
     min_step, preconditioning = _pop(min_step, "min_step"), _pop(preconditioning, "preconditioning")
     if not kwargs.get("backtracking", True):
         min_step = 1
+    if maxiter is None or int(maxiter) <= 0:
+        raise ValueError("maxiter must be a positive integer")  # the reference's loop would never stop (optimize.py:2183)
     orb._need_modes()
     L = _lib.lib()
     out = orb.copy()
