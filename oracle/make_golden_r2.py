@@ -130,16 +130,21 @@ def _cfg0_one(seed):
     return [seed, r1.status, r1.nit, r1.costs[-1], status, r.nit, r.costs[-1], r.orbit.t, r.orbit.x, t1 - t0, t2 - t1]
 
 
-def gen_cfg0(procs):
-    """BASELINE configs[0] (hunt(('adj','lstsq'), maxiter=[10000,200], tol=[1e-6,1e-10])) on OrbitKS 32x32 seeds 0..63:
-    per-seed table [seed, adj status, adj nit, adj cost, final status, lstsq nit, final cost, T, L, adj s, lstsq s]."""
+def gen_cfg0(procs, n_seeds=256):
+    """BASELINE configs[0] (hunt(('adj','lstsq'), maxiter=[10000,200], tol=[1e-6,1e-10])) on OrbitKS 32x32 seeds 0..n_seeds-1:
+    per-seed table [seed, adj status, adj nit, adj cost, final status, lstsq nit, final cost, T, L, adj s, lstsq s].  Rows already
+    in tests/golden/ks_cfg0_table.npz are kept (the runs are deterministic), so the table can be extended."""
     import multiprocessing as mp
 
+    path = os.path.join(GOLD, "ks_cfg0_table.npz")
+    rows = [list(r) for r in np.load(path)["table"]] if os.path.exists(path) else []
+    have = {int(r[0]) for r in rows}
+    todo = [s for s in range(n_seeds) if s not in have]
     with mp.get_context("fork").Pool(procs) as pool:
-        rows = []
-        for row in pool.imap(_cfg0_one, range(64)):
+        for row in pool.imap(_cfg0_one, todo):
             rows.append(row)
             print("cfg0", row, flush=True)
+    rows.sort(key=lambda r: r[0])
     np.savez_compressed(os.path.join(GOLD, "ks_cfg0_table.npz"), table=np.array(rows, dtype=float),
                         columns=np.array(["seed", "adj_status", "adj_nit", "adj_cost", "status", "lstsq_nit", "cost", "t", "x",
                                           "adj_seconds", "lstsq_seconds"]))
@@ -149,6 +154,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="cfg2,cfg3,square,lsq,deriv")
     ap.add_argument("--procs", type=int, default=os.cpu_count())
+    ap.add_argument("--cfg0-seeds", type=int, default=256)
     args = ap.parse_args()
     which = set(args.only.split(","))
     path = os.path.join(GOLD, "ks_hunt_r2.npz")
@@ -167,7 +173,7 @@ def main():
         np.savez_compressed(path, **out)
         print(path, os.path.getsize(path))
     if "cfg0" in which:
-        gen_cfg0(args.procs)
+        gen_cfg0(args.procs, args.cfg0_seeds)
 
 
 if __name__ == "__main__":
