@@ -141,7 +141,7 @@ def gen_cfg0(procs, n_seeds=256):
     have = {int(r[0]) for r in rows}
     todo = [s for s in range(n_seeds) if s not in have]
     with mp.get_context("fork").Pool(procs) as pool:
-        for row in pool.imap(_cfg0_one, todo):
+        for row in pool.imap_unordered(_cfg0_one, todo):
             rows.append(row)
             print("cfg0", row, flush=True)
     rows.sort(key=lambda r: r[0])
