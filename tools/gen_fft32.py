@@ -158,8 +158,18 @@ def cconst(r):
     return f"{'-' if r < 0 else ''}KS_FFT32_C({CONSTANTS.index(mag)}, {mag!r})"
 
 
+def by_level(ops):
+    """the same operations ordered by their depth in the dependency graph (independent operations next to each other)"""
+    depth = {}
+    for dst, kind, r, b, a in ops:
+        depth[dst] = 1 + max([depth.get(ref, 0) for ref in (a, b) if ref is not None and ref[0] == "t"] + [0])
+    return sorted(ops, key=lambda op: depth[op[0]])  # stable: generation order within a level
+
+
 def emit_body(ops):
     lines = []
+    if not os.environ.get("KS_FFT32_RECURSION_ORDER"):  # level order: 327 vs 334 us per 65 536 orbits (profiles/r02z_*)
+        ops = by_level(ops)
     for dst, kind, r, b, a in ops:
         if kind == "add":
             e = f"{cref(a)} + {cref(b)}"
