@@ -1,3 +1,9 @@
+"""Diagnostic behind tests/test_gpu_r2.py::test_cfg0_status_table_matches_reference: BASELINE configs[0] (adj 10000 -> lstsq 200)
+on the seeds of tests/golden/ks_cfg0_table.npz (the unmodified reference's outcomes), for several chunk / refinement settings of
+the dense step; prints the converged sets, their differences and the exit-code confusion matrix.
+
+    python tools/cfg0_diag.py      (on a GPU box, from the repository root)
+"""
 import os, sys, json
 import numpy as np
 sys.path.insert(0, os.getcwd())
