@@ -49,6 +49,11 @@ void ks_debug_warp32_pingpong(int on);
  * kernel (cross-check), 1 (default) = tile path with the CTA-resident fused kernel at 64x64, 2 = multi-pass tiles for
  * every shape; chunk_mb > 0 sets the workspace budget that bounds how many orbits one pass sequence covers. */
 void ks_debug_tile(int enabled, int chunk_mb);
+/* tuning hook, Newton-Krylov drivers at 64x64: 1 = N(u, u) is computed once per outer iteration and reused by every matvec /
+ * rmatvec of the inner solve (6 instead of 8 line-transform sweeps per operator application), identical bits; 0 (default) =
+ * every application recomputes it.  Measured at BASELINE configs[2]: -1 % (Relative) .. +7 % (Antisymmetric) on the
+ * Newton-GMRES(50) wall time (profiles/r02oc_operator_cache.jsonl), so it stays off. */
+void ks_debug_operator_cache(int on);
 /* tuning / test hook, multi-pass tile path: 0 (default) = one CTA per tile, loads into registers; 1 = the row and column
  * pass kernels are persistent and stage their tiles with the Tensor Memory Accelerator (cp.async.bulk.tensor boxes in and out,
  * cp.async.bulk lines, two-stage shared-memory ring on mbarriers); 2 / 3 = TMA rows only / columns only.  Bit-identical

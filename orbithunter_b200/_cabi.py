@@ -12,6 +12,7 @@ _SIG = {
     "ks_debug_tile": (None, [C.c_int, C.c_int]),
     "ks_debug_gmres_cluster": (None, [C.c_int]),
     "ks_debug_tile_tma": (None, [C.c_int]),
+    "ks_debug_operator_cache": (None, [C.c_int]),
     "ks_debug_adjoint_inner": (None, [C.c_int]),
     "ks_mode_size": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "ks_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -125,9 +125,11 @@ int dispatch(int cls, int n, int m, const KsEvalArgs& a, void* ws, size_t ws_byt
 }  // namespace
 
 int ks_tile_tma_mode() { return g_tile_tma; }
+int g_op_cache = 0;  // Krylov drivers: reuse N(u, u) across the operator applications of one inner solve (64x64); measured: -1 .. +7 %, off
 
 extern "C" {
 
+void ks_debug_operator_cache(int on) { g_op_cache = on != 0; }
 void ks_debug_tile_tma(int mode) { g_tile_tma = (mode >= 0 && mode <= 3) ? mode : 0; }
 int ks_b200_abi_version(void) { return 1; }
 const char* ks_last_error(void) { return g_err; }
@@ -617,6 +619,9 @@ NkLayout nk_layout(int cls, int n, int m, int batch, int method, int restart, ui
     take(batch * N * 8);                                      // 17 w vector
     take(batch * N * 8);                                      // 18 hbar (LSMR)
   }
+  // 19: operator cache (N(u, u)) where the CTA-resident 64x64 kernel runs the operator
+  const bool opc = g_op_cache && method != 3 && n == 64 && m == 64 && g_tile_mode == 1 && use_tile(n, m);
+  take(opc ? batch * nm * 8 : 8);
   L.total = p;
   return L;
 }
@@ -671,15 +676,18 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
   int* counters = reinterpret_cast<int*>(at(12));  // [0] solver active, [1] line search active, [2] live orbits
   if (check_every <= 0) check_every = 8;
   long long n_ops = 0, n_steps = 0, n_ls = 0, n_outer = 0;
+  const bool opc = g_op_cache && method != 3 && n == 64 && m == 64 && g_tile_mode == 1 && use_tile(n, m);
+  double* n_cache = opc ? reinterpret_cast<double*>(at(19)) : nullptr;
 
   auto poll = [&](int idx, int& value) -> bool {
     return cudaMemcpyAsync(&value, counters + idx, 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
            cudaStreamSynchronize(s) == cudaSuccess;
   };
-  auto eval_eqn = [&](const double* u, const double* up, double* f, double* c) {
+  auto eval_eqn = [&](const double* u, const double* up, double* f, double* c, bool fill_cache = false) {
     KsEvalArgs a;
     std::memset(&a, 0, sizeof(a));
     a.modes = u; a.params = up; a.out_state = f; a.out_cost = c; a.batch = batch;
+    if (fill_cache) a.n_out = n_cache;  // u is fixed until the line search: operator cache
     return dispatch<KS_OP_EQN>(cls, n, m, a, eval_ws, eval_bytes, stream);
   };
   auto op_matvec = [&](const double* v_cdof, double* y) {  // y = J v, v in cdof layout
@@ -687,6 +695,7 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
     std::memset(&a, 0, sizeof(a));
     a.modes = modes; a.params = params; a.vmodes = v_cdof; a.vparams = nullptr; a.out_state = y; a.batch = batch;
     a.cmask = cmask; a.v_ld = N; a.v_tail = 1;
+    a.n_cache = n_cache;
     ++n_ops;
     return dispatch<KS_OP_MATVEC>(cls, n, m, a, eval_ws, eval_bytes, stream);
   };
@@ -695,6 +704,7 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
     std::memset(&a, 0, sizeof(a));
     a.modes = modes; a.params = params; a.vmodes = y; a.out_state = w_cdof; a.batch = batch;
     a.cmask = cmask; a.out_ld = N; a.out_tail = 1;
+    a.n_cache = n_cache;
     ++n_ops;
     return dispatch<KS_OP_RMATVEC>(cls, n, m, a, eval_ws, eval_bytes, stream);
   };
@@ -834,7 +844,7 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
     if (n_live == 0) break;
     ++n_outer;
     // right-hand side: -F  (and A^T(-F) for the normal equations)
-    if ((rc = eval_eqn(modes, params, Fy, nullptr)) != 0) return rc;
+    if ((rc = eval_eqn(modes, params, Fy, nullptr, opc)) != 0) return rc;
     if (method == 3) {
       if ((rc = dense_step(n_live)) != 0) return rc;
     } else if (method == 0) {
@@ -917,6 +927,7 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
           std::memset(&a, 0, sizeof(a));
           a.modes = modes; a.params = params; a.vmodes = vin; a.out_state = wout; a.batch = batch; a.cmask = cmask;
           a.v_ld = N; a.out_ld = N; a.out_tail = 1;
+          a.n_cache = n_cache;
           ++n_ops;
           rc = dispatch<KS_OP_RMATVEC>(cls, n, m, a, eval_ws, eval_bytes, stream);
         } else {
@@ -924,6 +935,7 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
           std::memset(&a, 0, sizeof(a));
           a.modes = modes; a.params = params; a.vmodes = vin; a.out_state = wout; a.batch = batch; a.cmask = cmask;
           a.v_ld = N; a.v_tail = 1; a.out_ld = N;
+          a.n_cache = n_cache;
           ++n_ops;
           rc = dispatch<KS_OP_MATVEC>(cls, n, m, a, eval_ws, eval_bytes, stream);
         }

@@ -134,17 +134,31 @@ KS_DEVI Tup stage2_load(const OrbitCtx& c, const Geom& g, int j, int kp) {
   return (OP == KS_OP_MATVEC || OP == KS_OP_COSTGRAD) ? gload<CLS>(c.Fo, j, kp, g) : gload<CLS>(c.Vo, j, kp, g);
 }
 
+// N(u, u) = 1/2 Dx(u u) at (j, kp) from P, the true-scaled tuple of the forward transform of u u (projected on the class)
+template <int CLS>
+KS_DEVI Tup n_from_p(const OrbitCtx& c, const Geom& g, int j, int kp, const Tup& P) {
+  const double qn = 0.5 * (c.qbase * ((kp + 1) * (1.0 / g.m)));
+  Tup N{-qn * P.b1, -qn * P.b2, qn * P.a1, qn * P.a2};
+  gproject<CLS>(N, j);
+  return N;
+}
+template <int CLS, int OP>
+KS_DEVI void stage1_point_n(const OrbitCtx& c, const Geom& g, int j, int kp, const Tup& N, const Tup& Mt, const Tup& V, Tup& W,
+                            Sums& s);
 template <int CLS, int OP>
 KS_DEVI void stage1_point(const OrbitCtx& c, const Geom& g, int j, int kp, const Tup& P, const Tup& Mt, const Tup& V, Tup& W,
                           Sums& s) {
+  stage1_point_n<CLS, OP>(c, g, j, kp, n_from_p<CLS>(c, g, j, kp, P), Mt, V, W, s);
+}
+// the same with N(u, u) given (operator cache of the Krylov drivers, or n_from_p above)
+template <int CLS, int OP>
+KS_DEVI void stage1_point_n(const OrbitCtx& c, const Geom& g, int j, int kp, const Tup& N, const Tup& Mt, const Tup& V, Tup& W,
+                            Sums& s) {
   constexpr bool REL = (CLS == KS_RELATIVE);
   const double w = (j == 0) ? 0.0 : c.wbase * (j * (1.0 / g.n));
   const double q = c.qbase * ((kp + 1) * (1.0 / g.m));
   const double q2 = q * q, q4 = q2 * q2, d = q4 - q2, e = 2.0 * q2 - 4.0 * q4;
-  const double qn = 0.5 * q;
   const double sig = c.sig;
-  Tup N{-qn * P.b1, -qn * P.b2, qn * P.a1, qn * P.a2};
-  gproject<CLS>(N, j);
   if constexpr (OP == KS_OP_EQN || OP == KS_OP_COSTGRAD) {
     Tup F;
     F.a1 = fma(d, Mt.a1, fma(-w, Mt.a2, N.a1));

@@ -150,6 +150,12 @@ __global__ void __launch_bounds__(kF64Threads, 2) tile_fused64_kernel(const Tile
   for (int orbit = blockIdx.x; orbit < a.batch; orbit += gridDim.x) {
     const kspw::OrbitCtx c = kspw::make_ctx<CLS, OP>(a, g, orbit, ta.TU + (size_t)blockIdx.x * g.nm);
     const bool act = kl < K;
+    // operator cache (Krylov drivers): N(u, u) was stored by the eqn evaluation that opened the outer iteration, so the
+    // forward transforms of u u (the second half of phase B and the first half of phase C: 2 of the 8 line sweeps) are
+    // skipped.  (Caching u's field as well and skipping phases A and B altogether was measured and dropped: reading 32 KB of
+    // field per orbit from L2 / HBM is not overlapped with anything in this one-orbit-at-a-time kernel -- 235 us per 4096
+    // operator applications against 260 us uncached, profiles/r02oc_*.)
+    const bool cached = (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) && a.n_cache != nullptr;
     // A: u's tuples (kept in registers for stage 1) -> spectra -> XC
     Tup Mt[NIT];
 #pragma unroll
@@ -163,22 +169,40 @@ __global__ void __launch_bounds__(kF64Threads, 2) tile_fused64_kernel(const Tile
       for (int i = 0; i < NIT; ++i)
         if (act) Vt[i] = gload<CLS>(c.Vo, j0 + i * JS, kl, g);
     }
+    Tup Nt[(OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) ? NIT : 1];
+    if constexpr (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) {
+      if (cached) {
+        const double* Nc = a.n_cache + (size_t)orbit * g.nm;
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          Nt[i] = Tup{0.0, 0.0, 0.0, 0.0};
+          if (act) Nt[i] = gload<CLS>(Nc, j0 + i * JS, kl, g);
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NIT; ++i) spec_store(lk, j0 + i * JS, N, Mt[i]);
     __syncthreads();
     col_inverse();
-    // B: field of u, u*u
-    row_pass(std::integral_constant<int, MODE_SQ>{}, nuu);
+    // B: field of u, u*u (the latter only when its transform is wanted)
+    row_pass(std::integral_constant<int, MODE_SQ>{}, nuu && !cached);
     // C: stage 1
-    col_forward(!nuu);
+    if (!cached) col_forward(!nuu);
     kspw::Sums sm;
     if (act) {
 #pragma unroll
       for (int i = 0; i < NIT; ++i) {
         const int j = j0 + i * JS;
-        const Tup P = tuple_of_line(j);
         Tup W{0.0, 0.0, 0.0, 0.0};
-        kspw::stage1_point<CLS, OP>(c, g, j, kl, P, Mt[i], Vt[(OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) ? i : 0], W, sm);
+        if (cached) {
+          if constexpr (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) kspw::stage1_point_n<CLS, OP>(c, g, j, kl, Nt[i], Mt[i], Vt[i], W, sm);
+        } else {
+          const Tup Nn = kspw::n_from_p<CLS>(c, g, j, kl, tuple_of_line(j));
+          if constexpr (OP == KS_OP_EQN) {
+            if (a.n_out) kspw::gstore<CLS>(a.n_out + (size_t)orbit * g.nm, j, kl, g, Nn);  // fills the operator cache
+          }
+          kspw::stage1_point_n<CLS, OP>(c, g, j, kl, Nn, Mt[i], Vt[(OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) ? i : 0], W, sm);
+        }
         if constexpr (REINV) spec_store(lk, j, N, W);
       }
     }

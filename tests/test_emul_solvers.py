@@ -145,3 +145,30 @@ def test_dense_newton_matches_lstsq_oracle(cid):
         assert abs(cost[b] - st["cost"]) <= 1e-8 * max(1.0, st["cost"]), (b, cost[b], st["cost"])
         assert relerr(Mo[b], rm) < 1e-6 and np.allclose(po[b], rp, rtol=1e-7)
     assert cnt[3] >= 1 and cnt[1] >= B
+
+
+@pytest.mark.parametrize("cid,method", [(2, 0), (1, 1)])
+def test_operator_cache_of_the_64x64_krylov_driver_changes_no_bit(cid, method):
+    """Newton-GMRES / LSQR at 64x64 (CTA-resident kernel): with the operator cache (N(u, u) computed once per outer iteration,
+    the two forward transforms of u u skipped in every matvec / rmatvec; opt-in, ks_debug_operator_cache) and without it the
+    driver must return identical bits -- the cached tuples are the very values the uncached kernel recomputes."""
+    n = m = 64
+    B = 2
+    M = np.stack([ko.populate_state(60.0, 44.0, n, m, 3 + s, cid) for s in range(B)])
+    p = np.tile([60.0, 44.0, 0.3 if cid == 1 else 0.0], (B, 1))
+    cons = ko.default_constraints(cid)
+    cmask = sum(1 << i for i in range(3) if cons[i])
+    kw = dict(restart=3, inner=1, rtol=1e-5) if method == 0 else dict(inner=4, atol=1e-6)
+    out = {}
+    try:
+        for on in (1, 0):
+            E.lib().ks_debug_operator_cache(on)
+            out[on] = E.newton_krylov(cid, n, m, M, p, cmask, method, maxiter=1, **kw)
+    finally:
+        E.lib().ks_debug_operator_cache(0)
+    for a, b in zip(out[1][:5], out[0][:5]):
+        assert np.array_equal(a, b)
+    assert out[1][5][0] == out[0][5][0] > 0  # the same number of operator applications
+    rm, rp, st = ko.newton_krylov(M[0], p[0], cid, method="gmres" if method == 0 else "lsqr", maxiter=1,
+                                  scipy_kwargs=dict(restart=3, maxiter=1) if method == 0 else dict(iter_lim=4))
+    assert abs(out[1][4][0] - st["cost"]) <= 1e-9 * st["cost"] and relerr(out[1][0][0], rm) < 1e-9
