@@ -639,9 +639,11 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "ks_warp32x1_kernel<OrbitKS,COSTGRAD>",
                      "algorithmic_bytes_per_launch": BATCH * ALG_BYTES_PER_EVAL,
-                     "note": "binding resource is the fp64 pipe, not HBM: 1990 fp64 warp-instructions executed per eval (ncu "
-                             "sm__pipe_fp64_cycles_active; 63.7 k lane-ops) against a MEASURED DFMA peak of 63.5 lanes/clk/SM "
-                             "(profiles/r02a_fp64_peak.jsonl) put 100 % of the pipe at 290 M evals/s = 0.67 of this HBM roofline"},
+                     "note": "not HBM-bound: the kernel executes 1704 fp64 warp-instructions per eval (ncu; 54.5 k lane-ops), so at the "
+                             "MEASURED DFMA peak of 63.5 lanes/clk/SM (profiles/r02a_fp64_peak.jsonl) 100 % of the fp64 pipe is 339 M "
+                             "evals/s = 0.78 of this HBM roofline; measured pipe activity 51 %, the limiter is dependent-issue latency at "
+                             "two warps per scheduler (DESIGN.md section 4); 4096 orbits are 3.46 rounds of the 1184 resident warps, "
+                             "B = 65536 reaches 0.45-0.46 (other_shapes[0])"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * (NM + 3) * 8,
                 "d2h_bytes_per_step": BATCH * (NM + 3 + 1) * 8, "steps": e2e_steps},
         "gpu_launches": args.steps, "clocks": clocks.summary(), "checksum_cost_sum": checksum,
