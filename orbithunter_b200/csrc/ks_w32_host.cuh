@@ -47,7 +47,7 @@ int launch_warp32x1_pc(const KsEvalArgs& a, cudaStream_t s) {
   static DynSmemOptIn optin;
   if (!optin.ensure(kern, smem)) return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(warp32x1) failed");
   const int ctas = (a.batch + ksx1::kWarpsPerCta - 1) / ksx1::kWarpsPerCta;
-  const int sms = sm_count();
+  const int sms = sm_count() * ksx1::kCtasPerSm;
   const cudaError_t ce = KS_LAUNCH_PDL(kern, (unsigned)(ctas < sms ? ctas : sms), (unsigned)(ksx1::kWarpsPerCta * 32), (size_t)smem, s, a);
   if (ce != cudaSuccess) {
     static char msg[160];

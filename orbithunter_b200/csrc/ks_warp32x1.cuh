@@ -23,7 +23,12 @@ using ks::static_for;
 using ksfft::cos64;
 using ksfft::sin64;
 
+#ifdef KS_X1_WARPS_PER_CTA
+constexpr int kWarpsPerCta = KS_X1_WARPS_PER_CTA;  // tuning build: 4 -> two CTAs per SM, 2 -> four
+#else
 constexpr int kWarpsPerCta = 8;
+#endif
+constexpr int kCtasPerSm = 8 / kWarpsPerCta;
 constexpr int kTileDoubles = 32 * 15 * 2;  // XB tile of one orbit: 480 double2
 constexpr int kPackedDoubles = 16 * 32 * 2;  // per orbit, packed lane-major layout of the fused adjoint pass (below)
 constexpr int kStageDoubles = 31 * 32;      // cp.async landing zone for the next orbit's half tuples (lane-private slots)
@@ -113,7 +118,7 @@ KS_DEVI double warp_sum(double v) {
 }
 
 template <int CLS, int OP, bool PC>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 1) ks_warp32x1_kernel(const KsEvalArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_kernel(const KsEvalArgs a) {
   static_assert(OP == KS_OP_EQN || OP == KS_OP_COSTGRAD || OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI,
                 "eqn, costgrad and the fused adjoint steps");
   // ADJ : one adjoint-descent pass per launch (decide on the previous trial, evaluate the next), state in global memory.
