@@ -166,9 +166,43 @@ def by_level(ops):
     return sorted(ops, key=lambda op: depth[op[0]])  # stable: generation order within a level
 
 
+def by_height(ops):
+    """list schedule: among the operations whose operands are available, the one with the longest path to an output first"""
+    users, height = {}, {}
+    for op in ops:
+        for ref in (op[4], op[3]):
+            if ref is not None and ref[0] == "t":
+                users.setdefault(ref, []).append(op[0])
+    for op in reversed(ops):
+        height[op[0]] = 1 + max([height[u] for u in users.get(op[0], [])] + [0])
+    done, out, pending = set(), [], list(ops)
+    remaining_uses = {k: len(v) for k, v in users.items()}
+    frees = os.environ.get("KS_FFT32_TIE_BREAK") == "last_use"  # tie-break on operations that end an operand's life (no gain)
+    while pending:
+        ready = [op for op in pending if all(ref is None or ref[0] != "t" or ref in done for ref in (op[4], op[3]))]
+
+        def key(op):
+            last = sum(1 for ref in (op[4], op[3]) if ref is not None and ref[0] == "t" and remaining_uses.get(ref, 0) == 1)
+            return (height[op[0]], last) if frees else (height[op[0]],)
+
+        best = max(ready, key=key)
+        out.append(best)
+        done.add(best[0])
+        pending.remove(best)
+        for ref in (best[4], best[3]):
+            if ref is not None and ref[0] == "t":
+                remaining_uses[ref] -= 1
+    return out
+
+
 def emit_body(ops):
     lines = []
-    if not os.environ.get("KS_FFT32_RECURSION_ORDER"):  # level order: 327 vs 334 us per 65 536 orbits (profiles/r02z_*)
+    # ptxas keeps much of the source order: recursion order 334 us per 65 536 orbits, dependency-level order 327 us, longest
+    # path first 320.5 us (profiles/r02z_x1_fft_emission_order.jsonl)
+    order = os.environ.get("KS_FFT32_ORDER", "height")
+    if order == "height":
+        ops = by_height(ops)
+    elif order == "level":
         ops = by_level(ops)
     for dst, kind, r, b, a in ops:
         if kind == "add":
