@@ -17,6 +17,12 @@
 #include "ks_warp32x1.cuh"
 
 using namespace ksh;
+// setup copies / memsets of the solver drivers: surface a failing call where it happens (a bad pointer would otherwise
+// leave garbage in the solver state and be reported much later, by a poll)
+#define KS_CHECK_CUDA(call, what)                                                      \
+  do {                                                                                 \
+    if ((call) != cudaSuccess) return fail(KS_ERR_LAUNCH, what ": CUDA call failed");  \
+  } while (0)
 namespace {
 bool shape_ok(int cls, int n, int m) {
   return cls >= 0 && cls <= 3 && n >= 4 && m >= 4 && (n % 2 == 0) && (m % 2 == 0) && n <= 4096 && m <= 4096;
@@ -421,9 +427,9 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
     a.precond = preconditioning;
     KS_LAUNCH(adj_fused_init_kernel, (batch + 255) / 256, 256, 0, s, status_out, nit_out, A.live, A.cur, step_out, step_size, batch);
     KS_LAUNCH(adj_pack_kernel, batch, 128, 0, s, (const double*)modes, A.u[0], cls, batch, (int)nm);
-    cudaMemcpyAsync(A.p[0], params, (size_t)batch * 24, cudaMemcpyDeviceToDevice, s);
-    cudaMemsetAsync(A.g[0], 0, pbytes, s);
-    cudaMemsetAsync(A.gp[0], 0, (size_t)batch * 24, s);
+    KS_CHECK_CUDA(cudaMemcpyAsync(A.p[0], params, (size_t)batch * 24, cudaMemcpyDeviceToDevice, s), "solver driver setup");
+    KS_CHECK_CUDA(cudaMemsetAsync(A.g[0], 0, pbytes, s), "solver driver setup");
+    KS_CHECK_CUDA(cudaMemsetAsync(A.gp[0], 0, (size_t)batch * 24, s), "solver driver setup");
     const long max_passes = (long)maxiter + 1200;
     int passes = 0;
     if (g_adj_inner > 0) {
@@ -431,7 +437,7 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
       // counts an iteration or halves its step in each pass, so ceil(max_passes / inner) launches always suffice
       A.inner = g_adj_inner;
       for (long done = 0; done < max_passes + A.inner; done += A.inner) {
-        cudaMemsetAsync(A.n_live, 0, 4, s);
+        KS_CHECK_CUDA(cudaMemsetAsync(A.n_live, 0, 4, s), "solver driver setup");
         A.first = (done == 0) ? 1 : 0;
         const int rc = w32_run(cls, KS_OP_ADJMULTI, a, s);
         if (rc != 0) return rc;
@@ -446,7 +452,7 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
       return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "fused adjoint descent launch failed");
     }
     for (long it = 0; it < max_passes; ++it) {
-      cudaMemsetAsync(A.n_live, 0, 4, s);
+      KS_CHECK_CUDA(cudaMemsetAsync(A.n_live, 0, 4, s), "solver driver setup");
       A.first = (it == 0) ? 1 : 0;
       const int rc = w32_run(cls, KS_OP_ADJSTEP, a, s);
       if (rc != 0) return rc;
@@ -488,10 +494,10 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
   st.min_step = min_step;
   st.maxiter = maxiter;
   KS_LAUNCH(adj_init_kernel, (batch + 255) / 256, 256, 0, s, status_out, nit_out, st.live, step_out, step_size, batch);
-  cudaMemcpyAsync(st.tu, modes, batch * nm * 8, cudaMemcpyDeviceToDevice, s);
-  cudaMemcpyAsync(st.tup, params, (size_t)batch * 24, cudaMemcpyDeviceToDevice, s);
-  cudaMemsetAsync(st.g, 0, batch * nm * 8, s);
-  cudaMemsetAsync(st.gp, 0, (size_t)batch * 24, s);
+  KS_CHECK_CUDA(cudaMemcpyAsync(st.tu, modes, batch * nm * 8, cudaMemcpyDeviceToDevice, s), "solver driver setup");
+  KS_CHECK_CUDA(cudaMemcpyAsync(st.tup, params, (size_t)batch * 24, cudaMemcpyDeviceToDevice, s), "solver driver setup");
+  KS_CHECK_CUDA(cudaMemsetAsync(st.g, 0, batch * nm * 8, s), "solver driver setup");
+  KS_CHECK_CUDA(cudaMemsetAsync(st.gp, 0, (size_t)batch * 24, s), "solver driver setup");
   // every live orbit either counts an iteration or halves its step in each pass: steps halve at most ~1100 times
   // before underflow and far fewer before min_step, iterations stop at maxiter
   const long max_passes = (long)maxiter + 1200;
@@ -509,7 +515,7 @@ int ks_adjoint_descent(int cls, int n, int m, int batch, double* modes, double* 
     a.precond = preconditioning;
     const int rc = dispatch<KS_OP_COSTGRAD>(cls, n, m, a, eval_ws, eval_bytes, stream);
     if (rc != 0) return rc;
-    cudaMemsetAsync(st.n_live, 0, 4, s);
+    KS_CHECK_CUDA(cudaMemsetAsync(st.n_live, 0, 4, s), "solver driver setup");
     st.first = (it == 0) ? 1 : 0;
     KS_LAUNCH(ksadj::adj_commit_trial_kernel, batch, ksadj::kThreads, 0, s, st);
     ++passes;
@@ -771,7 +777,7 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
       }
       // G = J J^T, then G (+ lambda I) = L L^T; orbits whose factorisation breaks down are redone with a growing shift
       for (int attempt = 0; attempt < 5; ++attempt) {
-        cudaMemsetAsync(redo, 0, 4, s);
+        KS_CHECK_CUDA(cudaMemsetAsync(redo, 0, 4, s), "solver driver setup");
         KS_LAUNCH(ksd::lambda_kernel, (C + 255) / 256, 256, 0, s, (const double*)gmean, lambda, failf, redo, attempt, C);
         if (attempt > 0) {
           int n_redo = 0;
@@ -837,7 +843,7 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
   KS_LAUNCH(nk_init_kernel, (batch + 255) / 256, 256, 0, s, status_out, nit_out, live, searching, cost_out, tol, batch);
 
   for (int outer = 0; outer <= maxiter; ++outer) {
-    cudaMemsetAsync(counters, 0, 16, s);
+    KS_CHECK_CUDA(cudaMemsetAsync(counters, 0, 16, s), "solver driver setup");
     KS_LAUNCH(count_flags_kernel, (batch + 255) / 256, 256, 0, s, live, batch, counters + 2);
     int n_live = 0;
     if (!poll(2, n_live)) return fail(KS_ERR_LAUNCH, "newton-krylov: device error while polling");
@@ -886,7 +892,7 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
           if ((rc = op_matvec(vin, Fy)) != 0) return rc;
           if ((rc = op_rmatvec(Fy, wout)) != 0) return rc;
         }
-        cudaMemsetAsync(counters, 0, 4, s);
+        KS_CHECK_CUDA(cudaMemsetAsync(counters, 0, 4, s), "solver driver setup");
         if (gm_cluster > 0) {
           cudaError_t ce;
           if (gm_cluster == 1 && N <= 8 * kskry::kThreads)
@@ -940,7 +946,7 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
           rc = dispatch<KS_OP_MATVEC>(cls, n, m, a, eval_ws, eval_bytes, stream);
         }
         if (rc != 0) return rc;
-        cudaMemsetAsync(counters, 0, 4, s);
+        KS_CHECK_CUDA(cudaMemsetAsync(counters, 0, 4, s), "solver driver setup");
         KS_LAUNCH(kskry::lsqr_step_kernel, batch, kskry::kThreads, 0, s, g);
         ++n_steps;
       }
@@ -952,12 +958,12 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
     ns.n_searching = counters + 1; ns.B = batch; ns.nm = nm; ns.N = N; ns.maxiter = maxiter; ns.cmask = cmask;
     ns.tol = tol; ns.ftol = ftol; ns.min_step = min_step;
     ns.mode = 0;
-    cudaMemsetAsync(counters + 1, 0, 4, s);
+    KS_CHECK_CUDA(cudaMemsetAsync(counters + 1, 0, 4, s), "solver driver setup");
     KS_LAUNCH(kskry::newton_step_kernel, batch, kskry::kThreads, 0, s, ns);
     ns.mode = 1;
     for (int ls = 0; ls < 1200; ++ls) {
       if ((rc = eval_eqn(tu, tup, Fy, tcost)) != 0) return rc;
-      cudaMemsetAsync(counters + 1, 0, 4, s);
+      KS_CHECK_CUDA(cudaMemsetAsync(counters + 1, 0, 4, s), "solver driver setup");
       KS_LAUNCH(kskry::newton_step_kernel, batch, kskry::kThreads, 0, s, ns);
       ++n_ls;
       int still = 0;
