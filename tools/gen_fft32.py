@@ -195,12 +195,43 @@ def by_height(ops):
     return out
 
 
+def by_latency(ops, lat):
+    """list schedule against a latency model: an operation may issue `lat` slots after its operands; among those that may,
+    the one with the longest path to an output goes first; if none may, the one that becomes available soonest"""
+    users, height = {}, {}
+    for op in ops:
+        for ref in (op[4], op[3]):
+            if ref is not None and ref[0] == "t":
+                users.setdefault(ref, []).append(op[0])
+    for op in reversed(ops):
+        height[op[0]] = 1 + max([height[u] for u in users.get(op[0], [])] + [0])
+    issued, out, pending, slot = {}, [], list(ops), 0
+    while pending:
+        avail = []
+        for op in pending:
+            deps = [ref for ref in (op[4], op[3]) if ref is not None and ref[0] == "t"]
+            if all(d in issued for d in deps):
+                avail.append((max([issued[d] + lat for d in deps] + [0]), op))
+        ready = [op for t, op in avail if t <= slot]
+        if ready:
+            best = max(ready, key=lambda op: height[op[0]])
+        else:
+            best = min(avail, key=lambda to: (to[0], -height[to[1][0]]))[1]
+        out.append(best)
+        issued[best[0]] = slot
+        pending.remove(best)
+        slot += 1
+    return out
+
+
 def emit_body(ops):
     lines = []
     # ptxas keeps much of the source order: recursion order 334 us per 65 536 orbits, dependency-level order 327 us, longest
     # path first 320.5 us (profiles/r02z_x1_fft_emission_order.jsonl)
     order = os.environ.get("KS_FFT32_ORDER", "height")
-    if order == "height":
+    if order.startswith("latency"):
+        ops = by_latency(ops, int(order[7:] or 4))
+    elif order == "height":
         ops = by_height(ops)
     elif order == "level":
         ops = by_level(ops)
