@@ -230,3 +230,36 @@ def test_tma_staged_tile_kernels_match_the_plain_ones(cid, shape, B):
     oc, ogs, ogp, _ = ko.costgrad(M, p, cid)
     tol = max(1e-12, 64 * 2.2e-16 * (2 * np.pi * (m // 2 - 1) / 44.0) ** 4)  # the adjoint amplifies FFT round-off by q_max^4
     assert relerr(out[1][1], ogs) < tol and relerr(out[1][0], oc) < 1e-12
+
+
+@pytest.mark.parametrize("cid,shape", [(0, (32, 32)), (1, (64, 64)), (2, (16, 24)), (3, (128, 64))])
+def test_empty_and_single_orbit_batches(cid, shape):
+    """Edge cases of the batch axis on every kernel family (register-resident 32x32, CTA-resident 64x64, generic, multi-pass
+    tiles): an EMPTY batch goes through every entry point without a launch error and returns empty results; a batch of ONE
+    orbit gives the same numbers as that orbit inside a larger batch (no dependence on the neighbours or on the grid size)."""
+    from orbithunter_b200 import BatchedOrbitKS
+    from orbithunter_b200.optimize import hunt
+
+    n, m = shape
+    name = CLASS_NAMES[cid]
+    big = BatchedOrbitKS.from_seeds(np.arange(5), (60.0, 44.0, 0.2 if cid == 1 else 0.0), name, (n, m))
+    one = big._like(big.state[2:3].contiguous(), big.parameters[2:3].contiguous())
+    empty = big._like(big.state[:0].contiguous(), big.parameters[:0].contiguous())
+    # empty batch
+    assert empty.batch == 0 and BatchedOrbitKS.from_seeds([], (60.0, 44.0, 0.0), name, (n, m)).batch == 0
+    c, g = empty.costgrad()
+    assert c.shape == (0,) and g.state.shape == (0,) + tuple(big.state.shape[1:]) and g.parameters.shape == (0, 3)
+    assert empty.eqn().state.shape[0] == 0 and empty.matvec(empty).state.shape[0] == 0 and empty.rmatvec(empty).state.shape[0] == 0
+    assert empty.transform("field").state.shape == (0, n, m) and empty.resize(n + 2, m + 2).state.shape[0] == 0
+    assert empty.rescale(2.0).state.shape[0] == 0 and empty.preprocess_codes()[0].shape == (0,)
+    for method in ("adj", "gmres"):
+        r = hunt(empty, method, maxiter=3)
+        assert r.status.shape == (0,) and r.orbit.batch == 0
+    # a batch of one
+    cb, gb = big.costgrad()
+    c1, g1 = one.costgrad()
+    assert torch.equal(c1[0], cb[2]) and torch.equal(g1.state[0], gb.state[2]) and torch.equal(g1.parameters[0], gb.parameters[2])
+    assert torch.equal(one.eqn().state[0], big.eqn().state[2])
+    assert torch.equal(one.matvec(one).state[0], big.matvec(big).state[2])
+    rb, r1 = hunt(big, "adj", maxiter=25), hunt(one, "adj", maxiter=25)
+    assert int(r1.status[0]) == int(rb.status[2]) and int(r1.nit[0]) == int(rb.nit[2]) and torch.equal(r1.orbit.state[0], rb.orbit.state[2])
