@@ -37,10 +37,15 @@ const char* ks_last_error(void);
 /* test hook: route 32x32 through the generic-size kernel instead of the register-resident one (cross-check). */
 void ks_debug_force_generic(int on);
 /* tuning hook, 32x32 kernel build variant: 3 = two orbits per warp, 7 warps/SM, global reads staged with cp.async
- * (all ops); 4 (default) = one orbit per warp, 8 warps/SM, all state in registers (eqn and costgrad; other ops use 3);
- * 5 = one orbit per warp, 12 warps/SM, field rows stashed in shared memory (eqn and costgrad);
- * 6 = variant 4's work split with the two warps of each scheduler taking turns on the fp64 pipe (eqn and costgrad). */
+ * (all ops); 4 (default) = one orbit per warp, 8 warps/SM, all state in registers (all ops);
+ * 5 = one orbit per warp, 12 warps/SM, field rows stashed in shared memory (eqn and costgrad; other ops use 3);
+ * 6 = variant 4's work split with the two warps of each scheduler taking turns on the fp64 pipe (eqn and costgrad);
+ * 7 = variant 4 for eqn / costgrad, variant 3 for matvec / rmatvec (the default before the one-orbit-per-warp kernel
+ * learned those two ops). */
 void ks_debug_warp32_variant(int variant);
+/* tuning hook, dense Newton step at 32x32: 1 (default) = Jacobian columns by the one-orbit-per-warp kernel's Jacobian mode
+ * (unit vectors made in the kernel, orbit read in place); 0 = batched matvec over a stored identity and replicated orbits. */
+void ks_debug_dense_jacobian_mode(int on);
 /* tuning hook, 32x32 kernels: nanoseconds between the start of the warps that share one SM scheduler (default 0). */
 void ks_debug_warp32_stagger(int ns);
 /* tuning hook, 32x32 variant 6: 1 (default) = token passing between the two warp groups, 0 = free-running warps. */
@@ -116,6 +121,14 @@ int ks_transform(int cls, int n, int m, int batch, int from_basis, int to_basis,
 /* OrbitKS.eqn (ks/orbits.py:526-555) + Orbit.cost (core.py:986-1008): F(u) and 1/2 |F|^2 (cost may be NULL). */
 int ks_eqn(int cls, int n, int m, int batch, const double* modes, const double* params, double* f_out,
            double* cost_out, void* ws, size_t ws_bytes, void* stream);
+
+/* OrbitKS.jacobian (ks/orbits.py:557-657; Relative :2662-2760; ShiftReflection / Antisymmetric inherit): the dense Jacobian of
+ * every orbit of the batch, transposed: jac_t[b][col][:] is column `col` (state slots in cdof order, then the free
+ * parameters) -- J(u_b) applied to the unit vector of that slot.  32x32: one launch of the one-orbit-per-warp kernel, which
+ * makes the unit vectors itself; other sizes: one batched matvec over a stored identity per orbit. */
+size_t ks_jacobian_workspace_bytes(int cls, int n, int m, int batch, uint32_t cmask);
+int ks_jacobian(int cls, int n, int m, int batch, const double* modes, const double* params, uint32_t cmask, double* jac_t,
+                void* ws, size_t ws_bytes, void* stream);
 
 /* OrbitKS.matvec (ks/orbits.py:659-709; Relative :2623-2660): J(u) v, with vparams = (dT, dL, dS). */
 int ks_matvec(int cls, int n, int m, int batch, const double* modes, const double* params, const double* vmodes,

@@ -7,6 +7,7 @@ _SIG = {
     "ks_last_error": (C.c_char_p, []),
     "ks_debug_force_generic": (None, [C.c_int]),
     "ks_debug_warp32_variant": (None, [C.c_int]),
+    "ks_debug_dense_jacobian_mode": (None, [C.c_int]),
     "ks_debug_warp32_stagger": (None, [C.c_int]),
     "ks_debug_warp32_pingpong": (None, [C.c_int]),
     "ks_debug_tile": (None, [C.c_int, C.c_int]),
@@ -24,6 +25,8 @@ _SIG = {
     "ks_transform": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "ks_eqn": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "ks_matvec": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_uint32, _P, _P, C.c_size_t, _P]),
+    "ks_jacobian_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]),
+    "ks_jacobian": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_uint32, _P, _P, C.c_size_t, _P]),
     "ks_rmatvec": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_uint32, _P, _P, _P, C.c_size_t, _P]),
     "ks_costgrad": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_uint32, C.c_int, _P, _P, _P, _P, _P,
                               C.c_size_t, _P]),

@@ -225,6 +225,22 @@ class BatchedOrbitKS:
                    _ptr(out))
         return self._like(out)
 
+    def jacobian(self):
+        """Dense Jacobians of the whole batch (OrbitKS.jacobian, ks/orbits.py:557-657), as a [batch, Nm, cdof] tensor (a
+        transposed view of the column-major array ks_jacobian fills)."""
+        self._need_modes()
+        L = _lib.lib()
+        dev = self.state.device
+        nm = self.state.shape[1] * self.state.shape[2]
+        ncol = nm + len(self.free_indices())
+        out = torch.empty((self.batch, ncol, nm), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            ws = workspace(dev, L.ks_jacobian_workspace_bytes(self.cls_id, self.n, self.m, self.batch, self.cmask), stream)
+            _lib.check(L.ks_jacobian(self.cls_id, self.n, self.m, self.batch, _ptr(self.state), _ptr(self.parameters), self.cmask,
+                                     _ptr(out), ws.data_ptr(), ws.numel(), stream))
+        return out.transpose(1, 2)
+
     def rmatvec(self, other):
         self._need_modes()
         out = torch.empty_like(self.state)

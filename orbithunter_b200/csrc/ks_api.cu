@@ -30,8 +30,9 @@ bool shape_ok(int cls, int n, int m) {
 int g_w32_pingpong = 0;
 int g_w32_stagger_ns = 0;  // tuning: start delay between the warps of one scheduler in the 32x32 kernels
 bool g_force_generic = false;  // debug/test switch: route 32x32 through the generic kernel as a cross-check
-int g_warp32_variant = 4;  // 32x32 eqn / costgrad / adjoint descent: 4 = one orbit per warp (ks_warp32x1.cuh, default), 3 = two orbits per
-                           // warp (ks_warp32.cuh, which always serves matvec / rmatvec)
+int g_warp32_variant = 4;  // 32x32 kernels: 4 = one orbit per warp (ks_warp32x1.cuh, default), 3 = two orbits per warp (ks_warp32.cuh,
+                           // which also serves matvec / rmatvec for variants 5, 6, 7)
+int g_dense_jac_mode = 1;  // dense Newton step, 32x32: Jacobian columns by the x1 kernel's Jacobian mode (0: matvec over a stored identity)
 bool use_warp32(int n, int m) { return n == 32 && m == 32 && !g_force_generic; }
 int warp32_grid(int batch, int warps_per_cta) {
   const int npairs = (batch + 1) / 2;
@@ -149,7 +150,8 @@ void ks_debug_tile(int enabled, int chunk_mb) {
 }
 void ks_debug_warp32_pingpong(int mode) { g_w32_pingpong = mode; }
 void ks_debug_warp32_stagger(int ns) { g_w32_stagger_ns = ns < 0 ? 0 : ns; }
-void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant >= 3 && variant <= 6) ? variant : 4; }
+void ks_debug_dense_jacobian_mode(int on) { g_dense_jac_mode = on ? 1 : 0; }
+void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant >= 3 && variant <= 7) ? variant : 4; }
 
 int ks_mode_size(int cls, int n, int m) { return shape_ok(cls, n, m) ? (n - 1) * mode_cols(cls, m) : 0; }
 
@@ -205,6 +207,53 @@ int ks_matvec(int cls, int n, int m, int batch, const double* modes, const doubl
   a.batch = batch;
   a.cmask = cmask;
   return dispatch<KS_OP_MATVEC>(cls, n, m, a, ws, ws_bytes, stream);
+}
+
+static int fill_grid(size_t total) { return (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184); }
+static int jacobian_columns(int cls, int n, int m, uint32_t cmask) {
+  int nfree = 0;
+  for (int i = 0; i < 3; ++i) nfree += ks::free_slot(cmask | (cls == KS_RELATIVE ? 0u : (uint32_t)KS_FIX_S), i) >= 0 ? 1 : 0;
+  return (n - 1) * mode_cols(cls, m) + nfree;
+}
+
+size_t ks_jacobian_workspace_bytes(int cls, int n, int m, int batch, uint32_t cmask) {
+  if (!shape_ok(cls, n, m) || batch <= 0) return 0;
+  const size_t N = (size_t)jacobian_columns(cls, n, m, cmask), nm = (size_t)(n - 1) * mode_cols(cls, m);
+  if (use_warp32(n, m)) return ks_workspace_bytes(cls, n, m, (int)((size_t)batch * N < 0x7fffffffu ? (size_t)batch * N : 0x7fffffff));
+  // one orbit at a time: its copies, the parameter copies, the identity, then the evaluation workspace of N products
+  return ((N * nm + N * 3 + N * N) * 8 + 255) / 256 * 256 + ks_workspace_bytes(cls, n, m, (int)N);
+}
+
+int ks_jacobian(int cls, int n, int m, int batch, const double* modes, const double* params, uint32_t cmask, double* jac_t,
+                void* ws, size_t ws_bytes, void* stream) {
+  if (batch > 0 && (!modes || !params || !jac_t)) return fail(KS_ERR_ARG, "null array argument");
+  if (!shape_ok(cls, n, m)) return fail(KS_ERR_SHAPE, "unsupported discretization");
+  if (batch <= 0) return 0;
+  if (cls != KS_RELATIVE) cmask |= KS_FIX_S;
+  const int N = jacobian_columns(cls, n, m, cmask), nm = (n - 1) * mode_cols(cls, m);
+  if ((size_t)batch * N > 0x7fffffffu) return fail(KS_ERR_ARG, "ks_jacobian: batch * columns exceeds the evaluation index range");
+  if (ws_bytes < ks_jacobian_workspace_bytes(cls, n, m, batch, cmask)) return fail(KS_ERR_WORKSPACE, "ks_jacobian: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  KsEvalArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.cmask = cmask;
+  if (use_warp32(n, m)) {  // unit vectors made in the kernel, u read in place (ks_warp32x1.cuh, Jacobian mode)
+    a.modes = modes; a.params = params; a.out_state = jac_t; a.batch = batch * N; a.jac_ncol = N;
+    return dispatch<KS_OP_MATVEC>(cls, n, m, a, ws, ws_bytes, stream);
+  }
+  double* Urep = static_cast<double*>(ws);
+  double* Prep = Urep + (size_t)N * nm;
+  double* Vrep = Prep + (size_t)N * 3;
+  const size_t head = (((size_t)N * nm + (size_t)N * 3 + (size_t)N * N) * 8 + 255) / 256 * 256;
+  KS_LAUNCH(ksd::identity_kernel, fill_grid((size_t)N * N), 256, 0, s, Vrep, N, (size_t)N * N);
+  for (int b = 0; b < batch; ++b) {
+    KS_LAUNCH(ksd::replicate_kernel, fill_grid((size_t)N * nm), 256, 0, s, modes + (size_t)b * nm, Urep, nm, N, (size_t)N * nm);
+    KS_LAUNCH(ksd::replicate_kernel, 8, 256, 0, s, params + (size_t)b * 3, Prep, 3, N, (size_t)N * 3);
+    a.modes = Urep; a.params = Prep; a.vmodes = Vrep; a.out_state = jac_t + (size_t)b * N * nm; a.batch = N; a.v_ld = N; a.v_tail = 1;
+    const int rc = dispatch<KS_OP_MATVEC>(cls, n, m, a, static_cast<char*>(ws) + head, ws_bytes - head, stream);
+    if (rc != 0) return rc;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "ks_jacobian: kernel launch failed");
 }
 
 int ks_rmatvec(int cls, int n, int m, int batch, const double* modes, const double* params, const double* vmodes,
@@ -762,12 +811,20 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
       const int* idx = d_idx + c0;
       KS_LAUNCH(ksd::gather_kernel, C, 256, 0, s, idx, (const double*)modes, (const double*)params, (const double*)Fy, Uc, Pc, rhs0, nm);
       // Jacobian: one batched matvec over the identity; column `col` of orbit c is evaluation number c * N + col
-      double* Urep = Lf;
-      double* Vrep = G;
-      KS_LAUNCH(ksd::replicate_kernel, 1184, 256, 0, s, (const double*)Uc, Urep, nm, N, (size_t)C * N * nm);
-      KS_LAUNCH(ksd::replicate_kernel, 296, 256, 0, s, (const double*)Pc, Prep, 3, N, (size_t)C * N * 3);
-      KS_LAUNCH(ksd::identity_kernel, 1184, 256, 0, s, Vrep, N, (size_t)C * N * N);
-      {
+      if (use_warp32(n, m) && g_dense_jac_mode) {
+        // 32x32: the one-orbit-per-warp kernel builds the unit vectors itself and reads u / parameters of orbit c for
+        // every column (no replicated copies, no identity in memory)
+        KsEvalArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.modes = Uc; a.params = Pc; a.out_state = J; a.batch = C * N; a.cmask = cmask; a.jac_ncol = N;
+        n_ops += N;
+        if ((rc_dense = dispatch<KS_OP_MATVEC>(cls, n, m, a, jws, jws_bytes, stream)) != 0) return rc_dense;
+      } else {
+        double* Urep = Lf;
+        double* Vrep = G;
+        KS_LAUNCH(ksd::replicate_kernel, 1184, 256, 0, s, (const double*)Uc, Urep, nm, N, (size_t)C * N * nm);
+        KS_LAUNCH(ksd::replicate_kernel, 296, 256, 0, s, (const double*)Pc, Prep, 3, N, (size_t)C * N * 3);
+        KS_LAUNCH(ksd::identity_kernel, 1184, 256, 0, s, Vrep, N, (size_t)C * N * N);
         KsEvalArgs a;
         std::memset(&a, 0, sizeof(a));
         a.modes = Urep; a.params = Prep; a.vmodes = Vrep; a.vparams = nullptr; a.out_state = J; a.batch = C * N;

@@ -49,7 +49,12 @@ struct Plan<256> {
 KS_HD constexpr bool size_ok(int v) { return v == 64 || v == 128 || v == 256; }
 
 // exp(-2 pi i j / N) at g_tw[N + j], N = 16 .. 256 (filled once per device by tw_init_kernel)
-static __device__ double2 g_tw[512];
+#ifdef KS_HOST_EMUL
+// one table for all translation units: the host linker keeps a single copy of the inline member functions that read it
+inline double2 g_tw[512];
+#else
+static __device__ double2 g_tw[512];  // per translation unit (no relocatable device code); each unit fills its own
+#endif
 static __global__ void tw_init_kernel(int) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < 16 || idx >= 512) return;

@@ -43,7 +43,7 @@ int launch_warp32_as(const KsEvalArgs& a, cudaStream_t s) {
 template <int CLS, int OP, bool PC>
 int launch_warp32x1_pc(const KsEvalArgs& a, cudaStream_t s) {
   auto kern = ksx1::ks_warp32x1_kernel<CLS, OP, PC>;
-  constexpr int smem = ksx1::smem_bytes(OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI);
+  constexpr int smem = ksx1::smem_bytes(OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI, OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC);
   static DynSmemOptIn optin;
   if (!optin.ensure(kern, smem)) return fail(KS_ERR_LAUNCH, "cudaFuncSetAttribute(warp32x1) failed");
   const int ctas = (a.batch + ksx1::kWarpsPerCta - 1) / ksx1::kWarpsPerCta;
@@ -113,12 +113,17 @@ int launch_warp32(int variant, const KsEvalArgs& a, cudaStream_t s) {
       }
       return launch_warp32x3_pc<CLS, OP, false>(a, s);
     }
-    if (variant == 4) {
+    if (variant == 4 || variant == 7) {
       if constexpr (OP == KS_OP_COSTGRAD) {
         if (a.precond) return launch_warp32x1_pc<CLS, OP, true>(a, s);
       }
       return launch_warp32x1_pc<CLS, OP, false>(a, s);
     }
+  }
+  if constexpr (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) {
+    // variant 4 (default): matvec / rmatvec on the one-orbit-per-warp kernel too (variant 7 keeps them on the two-orbits-per-warp
+    // kernel); the Jacobian mode (jac_ncol > 0) exists only there
+    if (variant == 4 || a.jac_ncol > 0) return launch_warp32x1_pc<CLS, OP, false>(a, s);
   }
   return launch_warp32_as<CLS, OP>(a, s);
 }

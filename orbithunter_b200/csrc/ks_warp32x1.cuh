@@ -40,9 +40,12 @@ constexpr bool kPark = true;
 #else
 constexpr bool kPark = false;
 #endif
-// adj: u and g, packed; otherwise the landing zone and (kPark) a second lane-private area of the same size
-KS_HD constexpr int warp_smem_doubles(bool adj) { return kTileDoubles + (adj ? 2 * kPackedDoubles : (kPark ? 2 : 1) * kStageDoubles); }
-KS_HD constexpr int smem_bytes(bool adj) { return kWarpsPerCta * warp_smem_doubles(adj) * 8; }
+// adj: u and g, packed; otherwise the landing zone of u and -- for matvec / rmatvec (v's landing zone) or kPark -- a second
+// lane-private area of the same size
+KS_HD constexpr int warp_smem_doubles(bool adj, bool vop = false) {
+  return kTileDoubles + (adj ? 2 * kPackedDoubles : ((kPark || vop) ? 2 : 1) * kStageDoubles);
+}
+KS_HD constexpr int smem_bytes(bool adj, bool vop = false) { return kWarpsPerCta * warp_smem_doubles(adj, vop) * 8; }
 
 // x[32] real -> c0 = DFT32(x)[0], (cr, ci)[k] = DFT32(x)[k], k = 1..15   (forward sign e^{-i...}, unnormalised).
 // ks_warp32.cuh's convention has the k >= 1 outputs doubled; here that factor (x2 per forward transform, x4 for the two
@@ -119,8 +122,9 @@ KS_DEVI double warp_sum(double v) {
 
 template <int CLS, int OP, bool PC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_kernel(const KsEvalArgs a) {
-  static_assert(OP == KS_OP_EQN || OP == KS_OP_COSTGRAD || OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI,
-                "eqn, costgrad and the fused adjoint steps");
+  static_assert(OP == KS_OP_EQN || OP == KS_OP_COSTGRAD || OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI || OP == KS_OP_MATVEC ||
+                    OP == KS_OP_RMATVEC,
+                "eqn, costgrad, matvec, rmatvec and the fused adjoint steps");
   // ADJ : one adjoint-descent pass per launch (decide on the previous trial, evaluate the next), state in global memory.
   // ADJM: every orbit runs up to adj.inner passes inside one launch; its accepted point u and gradient g stay in the
   //       warp's shared-memory stage (lane-private packed slots), the scalars in registers; the decision on a trial is
@@ -128,7 +132,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
   constexpr bool ADJ = (OP == KS_OP_ADJSTEP);
   constexpr bool ADJM = (OP == KS_OP_ADJMULTI);
   constexpr bool GRAD = (OP == KS_OP_COSTGRAD) || ADJ || ADJM;
-  constexpr int kWarpSmemDoubles = warp_smem_doubles(ADJ || ADJM);
+  // matvec / rmatvec (ks/orbits.py:659-755): the same five phases; stage 1 works on v's half tuples (landed in the second
+  // lane-private area, or generated as a unit vector in Jacobian mode) instead of forming F
+  constexpr bool MV = (OP == KS_OP_MATVEC), RMV = (OP == KS_OP_RMATVEC), VOP = MV || RMV;
+  constexpr int kWarpSmemDoubles = warp_smem_doubles(ADJ || ADJM, VOP);
   constexpr bool FULL = (CLS == KS_ORBIT || CLS == KS_RELATIVE);
   constexpr bool REL = (CLS == KS_RELATIVE);
   constexpr int COLS = FULL ? 30 : 15, NM = 31 * COLS;
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
   // the 31 half tuples of u (needed again in stage 1) resp. F (needed again in stage 2) used to sit in 62 registers right
   // through them.  Now u is re-read from the landing zone in phase C -- the next orbit's prefetch is issued only then, which
   // still leaves it half an orbit to land -- and F waits in a second lane-private area until phase E.
-  constexpr bool PARK = kPark && !(OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI);
+  constexpr bool PARK = kPark && !(OP == KS_OP_ADJSTEP || OP == KS_OP_ADJMULTI) && !VOP;
   double* park = tile + kTileDoubles + kStageDoubles + lane;  // slot s of this lane at park[s * 32]
   const int c = lane >> 1, h = lane & 1;
   const bool colact = c < 15;
@@ -156,6 +163,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
   constexpr double cN = 0.5 / (64.0 * 4096.0), cP = 1.0 / (64.0 * 4096.0);
   // column offset of this lane's half inside a modes row: full classes [Re_x | Im_x], half classes a single block
   const int coff = (FULL ? h * 15 : 0) + cc;
+  const int jac = VOP ? a.jac_ncol : 0;  // Jacobian mode: evaluation e = (orbit e / jac, column e % jac)
+  const int v_ld = a.v_ld ? a.v_ld : NM;
+  auto uidx = [&](int e) { return jac > 0 ? e / jac : e; };
 
   // u's half tuples reach the registers through a cp.async landing zone filled one orbit ahead (the first-touch DRAM
   // latency of the modes was 26 % of the warp-issue samples with plain loads: profiles/r01g_*)
@@ -222,9 +232,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
       }
     } else {
       pd.live = 1;
-      pd.T = a.params[orb * 3 + 0];
-      pd.L = a.params[orb * 3 + 1];
-      pd.S = a.params[orb * 3 + 2];
+      pd.T = a.params[uidx(orb) * 3 + 0];
+      pd.L = a.params[uidx(orb) * 3 + 1];
+      pd.S = a.params[uidx(orb) * 3 + 2];
     }
     return pd;
   };
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
           cp_async16(pstage + kPackedDoubles + pr * 64, Gn + pr * 64);
         }
       } else {
-        const double* Mn = a.modes + (size_t)orb * NM + coff;
+        const double* Mn = a.modes + (size_t)uidx(orb) * NM + coff;
         static_for<0, 16>([&](auto Jc) {
           constexpr int J = decltype(Jc)::value;
           const bool pres = (J & 1) ? presO : presE;
@@ -252,6 +262,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
     }
     ksw32::cp_async_commit();
   };
+  // matvec / rmatvec: v's half tuples land in the second lane-private area (same slots as u's); issued once phase C has read
+  // the current orbit's v.  Jacobian mode has no v in memory.
+  [[maybe_unused]] auto prefetch_v = [&](int orb) {
+    if constexpr (VOP) {
+      if (orb < a.batch && jac == 0) {
+        const double* Vn = a.vmodes + (size_t)orb * v_ld + coff;
+        static_for<0, 16>([&](auto Jc) {
+          constexpr int J = decltype(Jc)::value;
+          const bool pres = (J & 1) ? presO : presE;
+          if (pres) {
+            ksw32::cp_async8(park + (J == 0 ? 0 : 2 * J - 1) * 32, Vn + J * COLS);
+            if constexpr (J > 0) ksw32::cp_async8(park + (2 * J) * 32, Vn + (15 + J) * COLS);
+          }
+        });
+      }
+      ksw32::cp_async_commit();
+    }
+  };
   // programmatic dependent launch: everything above overlapped the previous kernel's tail; nothing below may run before
   // that kernel's writes are visible
   ks_pdl_launch_dependents();
@@ -263,6 +291,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
   if constexpr (!ADJM) {
     next = decide(gw);
     prefetch(gw, next);
+    prefetch_v(gw);
   }
 #pragma unroll 1
   for (int orbit = gw; orbit < a.batch; orbit += nw) {
@@ -397,6 +426,48 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
     __syncwarp();
     // ---------------- phase C (COL): N = 1/2 Dx(.) via the other component; stage 1; W = Dx F via the store ----------------
     double s_ff = 0.0, s_mf = 0.0, s_x = 0.0, s_d = 0.0;
+    [[maybe_unused]] double s_nv = 0.0;
+    // matvec: the parameter components of v, pre-scaled (-1/T, 1/L, -1/T) as in ks_warp32.cuh; Jacobian mode: unit vector of
+    // column e % jac -- state slot (jrow, jcol) of the modes array or parameter slot jpar
+    [[maybe_unused]] double vt = 0.0, vx = 0.0, vs = 0.0;
+    [[maybe_unused]] int jrow = -1, jcol = -1;
+    if constexpr (VOP) {
+      int jpar = -1;
+      if (jac > 0) {
+        const int col = orbit % jac;
+        if (col < NM) {
+          jrow = col / COLS;
+          jcol = col - jrow * COLS;
+        } else {
+          jpar = col - NM;
+        }
+      }
+      if constexpr (MV) {
+        double v3[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int slot = ks::free_slot(a.cmask, i);
+          if (jac > 0) v3[i] = (slot >= 0 && slot == jpar) ? 1.0 : 0.0;
+          else v3[i] = a.v_tail ? (slot < 0 ? 0.0 : a.vmodes[(size_t)orbit * v_ld + NM + slot]) : a.vparams[orbit * 3 + i];
+        }
+        vt = fix_t ? 0.0 : v3[0] * (-1.0 / T);
+        vx = fix_x ? 0.0 : v3[1] * (1.0 / Lx);
+        vs = fix_s ? 0.0 : v3[2] * (-1.0 / T);
+      }
+    }
+    // this lane's half tuple J of v
+    [[maybe_unused]] auto vhalf = [&](auto Jc, double& v1, double& v2) {
+      constexpr int J = decltype(Jc)::value;
+      const bool pres = (J & 1) ? presO : presE;
+      if (jac > 0) {
+        const bool mine = pres && colact && jcol == coff;
+        v1 = (mine && jrow == J) ? 1.0 : 0.0;
+        v2 = (J > 0 && mine && jrow == 15 + J) ? 1.0 : 0.0;
+      } else {
+        v1 = pres ? park[(J == 0 ? 0 : 2 * J - 1) * 32] : 0.0;
+        if constexpr (J > 0) v2 = pres ? park[(2 * J) * 32] : 0.0; else v2 = 0.0;
+      }
+    };
     {
       double x[32];
       const double scl = 4.0 * sgq * cN;
@@ -420,6 +491,40 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
         const bool pres = (J & 1) ? presO : presE;
         const double w = (J == 0) ? 0.0 : wbase * (J * (1.0 / 32.0));
         const double u1 = m1[J], u2 = m2[J];
+        if constexpr (VOP) {
+          double v1, v2;
+          vhalf(Jc, v1, v2);
+          if constexpr (RMV) {  // sums of J^T v's parameter components (ks/orbits.py:2004-2020, :3064-3092); stage 2 acts on v
+            s_mf = fma(u1, v1, fma(u2, v2, s_mf));
+            s_x = fma(w, fma(u1, v2, -u2 * v1), s_x);
+            s_nv = fma(nr[J], v1, fma(ni[J], v2, s_nv));
+            if constexpr (REL) {
+              const double p1 = __shfl_xor_sync(0xffffffffu, u1, 1), p2 = __shfl_xor_sync(0xffffffffu, u2, 1);
+              s_d += sgq * (p1 * v1 + p2 * v2);
+            }
+            m1[J] = v1;
+            m2[J] = v2;
+          } else {  // matvec: everything except the u * v product (ks/orbits.py:690-707, :2648-2658)
+            const double e = 2.0 * q2 - 4.0 * q4, ce = vx * e, cdt = vt * w;
+            double r1 = fma(d, v1, -w * v2), r2 = fma(d, v2, w * v1);
+            if constexpr (REL) {
+              const double pv1 = __shfl_xor_sync(0xffffffffu, v1, 1), pv2 = __shfl_xor_sync(0xffffffffu, v2, 1);
+              r1 = fma(-sig * sgq, pv1, r1);
+              r2 = fma(-sig * sgq, pv2, r2);
+            }
+            r1 += fma(ce, u1, fma(-cdt, u2, -vx * nr[J]));
+            r2 += fma(ce, u2, fma(cdt, u1, -vx * ni[J]));
+            if constexpr (REL) {
+              const double cdxs = (-sig * vt + sig * vx + vs) * sgq;
+              const double pu1 = __shfl_xor_sync(0xffffffffu, u1, 1), pu2 = __shfl_xor_sync(0xffffffffu, u2, 1);
+              r1 = fma(cdxs, pu1, r1);
+              r2 = fma(cdxs, pu2, r2);
+            }
+            m1[J] = pres ? r1 : 0.0;
+            m2[J] = (pres && J > 0) ? r2 : 0.0;
+          }
+          return;
+        }
         double f1 = fma(d, u1, fma(-w, u2, nr[J]));
         double f2 = (J == 0) ? 0.0 : fma(d, u2, fma(w, u1, ni[J]));
         if constexpr (REL) {  // - (S/T) dx(u): a += sig q b, b -= sig q a  (partner's half via shuffle)
@@ -467,7 +572,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
       }
       // reductions over the 30 active lanes
       const double lw = colact ? 1.0 : 0.0;
-      const double ff = warp_sum(s_ff * lw);
+      const double ff = VOP ? 0.0 : warp_sum(s_ff * lw);
       if constexpr (ADJ) {
         if (lane == 0) {
           const KsAdjFused& A = a.adj;
@@ -484,13 +589,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
         }
       } else if constexpr (ADJM) {
         ct = 0.5 * ff;
-      } else {
+      } else if constexpr (!VOP) {
         if (lane == 0 && a.out_cost) a.out_cost[orbit] = 0.5 * ff;
       }
-      if constexpr (GRAD) {
+      if constexpr (GRAD || RMV) {
         const double e = 2.0 * q2 - 4.0 * q4;
         // with <dx u, F> = s_d (summed over both halves): r_t ~ s_x - sig s_d, r_x ~ (e+d) s_mf + s_x - s_ff, r_s ~ s_d
-        double px = warp_sum(fma(e + d, s_mf, s_x - s_ff) * lw);
+        // (rmatvec: no identity for <N, v>: r_x ~ e s_mf + sig s_d - <N, v>)
+        double px = warp_sum((RMV ? fma(e, s_mf, fma(sig, s_d, -s_nv)) : fma(e + d, s_mf, s_x - s_ff)) * lw);
         double pt = warp_sum(fma(-sig, s_d, s_x) * lw);
         double ps = REL ? warp_sum(s_d * lw) : 0.0;
         if (ADJM || (lane == 0 && (ADJ || a.out_params || a.out_tail))) {
@@ -534,19 +640,36 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
       // second inverse: spectrum of F's half -> its field component; Dx F = iq (A_F + i B_F): h0 writes q A_F to .y,
       // h1 writes -q B_F to .x
       double hr[16], hi[16];
+      double h0 = m1[0];
+      if constexpr (MV) {  // matvec: the second field is v itself (m1 / m2 hold the stage-1 result until phase E)
+        double unused;
+        vhalf(std::integral_constant<int, 0>{}, h0, unused);
+        static_for<1, 16>([&](auto Jc) { vhalf(Jc, hr[decltype(Jc)::value], hi[decltype(Jc)::value]); });
+      } else {
 #pragma unroll
-      for (int J = 1; J < 16; ++J) {
-        hr[J] = m1[J];
-        hi[J] = m2[J];
+        for (int J = 1; J < 16; ++J) {
+          hr[J] = m1[J];
+          hi[J] = m2[J];
+        }
       }
+      if constexpr (VOP) prefetch_v(orbit + nw);  // v has left its landing zone
       hr[0] = hi[0] = 0.0;
-      irfft32(ks::kSqrt2 * m1[0], hr, hi, x);
+      irfft32(ks::kSqrt2 * h0, hr, hi, x);
       // everything between this store and the load of phase E is linear, so phase E's power-of-two normalisation 4 cP rides
       // along here (exact: same bits as scaling there)
-      const double sw = (h ? -q : q) * (4.0 * cP);
-      if (colact) {
+      if constexpr (MV) {
+        // this lane read component 1 - h at the top of the phase, which is the component its partner lane stores now
+        __syncwarp();
+        if (colact) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) tile[(t * 15 + c) * 2 + (1 - h)] = sw * x[t];
+          for (int t = 0; t < 32; ++t) tile[(t * 15 + c) * 2 + h] = (4.0 * cP) * x[t];
+        }
+      } else {
+        const double sw = (h ? -q : q) * (4.0 * cP);
+        if (colact) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) tile[(t * 15 + c) * 2 + (1 - h)] = sw * x[t];
+        }
       }
     }
     __syncwarp();
@@ -576,7 +699,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
     {
       double x[32];
 #pragma unroll
-      for (int t = 0; t < 32; ++t) x[t] = tile[(t * 15 + cc) * 2 + h];
+      for (int t = 0; t < 32; ++t) x[t] = tile[(t * 15 + cc) * 2 + (MV ? 1 - h : h)];  // matvec: Dx(u v) crosses the halves
       double p0, pr[16], pi[16];
       rfft32_fwd(x, p0, pr, pi);
       pr[0] = (0.5 * ks::kSqrt2) * p0;
@@ -597,7 +720,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
         }
         double g1 = fma(d, f1, fma(w, f2, -pr[J]));
         double g2 = (J == 0) ? 0.0 : fma(d, f2, fma(-w, f1, -pi[J]));
-        if constexpr (REL) {  // + (S/T) dx(F)
+        if constexpr (MV) {  // + 2 * 1/2 Dx(u v) (ks/orbits.py:692)
+          g1 = fma(sgq, pr[J], f1);
+          g2 = (J == 0) ? 0.0 : fma(sgq, pi[J], f2);
+        }
+        if constexpr (REL && !MV) {  // + (S/T) dx(F)
           const double p1 = __shfl_xor_sync(0xffffffffu, f1, 1), p2 = __shfl_xor_sync(0xffffffffu, f2, 1);
           g1 = fma(sig * sgq, p1, g1);
           if constexpr (J > 0) g2 = fma(sig * sgq, p2, g2);

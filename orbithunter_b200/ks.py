@@ -321,22 +321,10 @@ class OrbitKS:
         return LinearOperator(shape=(diag.size, diag.size), matvec=mv, rmatvec=mv, matmat=mm, rmatmat=mm)
 
     def jacobian(self, **kwargs):
-        """Dense (Nm x cdof) Jacobian (ks/orbits.py:557-657): one batched matvec over the identity, on the GPU."""
+        """Dense (Nm x cdof) Jacobian (ks/orbits.py:557-657): every column is one matvec against a unit vector, all in one
+        launch on the GPU (ks_jacobian)."""
         assert self.basis == "modes", "Convert to spatiotemporal Fourier mode basis before computing Jacobian"
-        nm = self.state.size
-        free = [i for i, lab in enumerate(self.parameter_labels()) if not self.constraints[lab]]
-        ncol = nm + len(free)
-        v = np.zeros((ncol, nm))
-        v[np.arange(nm), np.arange(nm)] = 1.0
-        vp = np.zeros((ncol, 3))
-        for slot, i in enumerate(free):
-            vp[nm + slot, i] = 1.0
-        ub = BatchedOrbitKS(torch.as_tensor(np.broadcast_to(self.state, (ncol,) + self.state.shape).copy()),
-                            torch.as_tensor(np.broadcast_to(np.asarray(self.parameters), (ncol, 3)).copy()), self._cls_id(),
-                            "modes", self.discretization, self.constraints)
-        vb = BatchedOrbitKS(torch.as_tensor(v.reshape((ncol,) + self.state.shape)), torch.as_tensor(vp), self._cls_id(), "modes",
-                            self.discretization, self.constraints)
-        return ub.matvec(vb).state.reshape(ncol, nm).T.contiguous().cpu().numpy()
+        return self._host(self._batched(basis="modes").jacobian().contiguous())
 
     # ---- vector packing (core.py:1617-1664, :1760-1796; ks/orbits.py:305-377) ----------------------------------------
     def cdof(self):

@@ -88,6 +88,19 @@ def matvec(cls, n, m, modes, params, v, vp, cmask):
     return out
 
 
+def jacobian(cls, n, m, modes, params, cmask):
+    """[B, cdof, Nm]: column-major Jacobians."""
+    L = lib()
+    modes, params = (np.ascontiguousarray(x, dtype=float) for x in (modes, params))
+    B, nm = modes.shape[0], modes.shape[1] * modes.shape[2]
+    ncol = nm + sum(1 for i in range(3) if not (cmask >> i) & 1)
+    out = np.zeros((B, ncol, nm))
+    nb = L.ks_jacobian_workspace_bytes(cls, n, m, B, cmask)
+    ws = np.zeros(nb // 8 + 1)
+    _chk(L, L.ks_jacobian(cls, n, m, B, _p(modes), _p(params), cmask, _p(out), _p(ws), nb, None))
+    return out
+
+
 def rmatvec(cls, n, m, modes, params, v, cmask):
     L = lib()
     modes, params, v = (np.ascontiguousarray(x, dtype=float) for x in (modes, params, v))

@@ -48,7 +48,7 @@ def _check_all_ops(cid, n, m, B, cons):
     assert np.allclose(rp, orp, rtol=1e-11, atol=1e-11 * max(np.max(np.abs(orp)), 1e-300))
 
 
-@pytest.mark.parametrize("variant", [3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [3, 4, 5, 6, 7])
 @pytest.mark.parametrize("cid", range(4))
 def test_warp32_kernel_all_ops(cid, variant):
     E.lib().ks_debug_force_generic(0)
@@ -160,3 +160,30 @@ def test_device_seed_generator_matches_reference_stream(cid, shape):
     for i, s in enumerate(seeds):
         ref = ko.populate_state(params[i, 0], params[i, 1], n, m, int(s), cid)
         assert relerr(out[i], ref) < 1e-14
+
+
+@pytest.mark.parametrize("cid,shape", [(1, (32, 32)), (2, (32, 32)), (1, (8, 10)), (2, (6, 8))])
+def test_jacobian_columns_match_oracle_matvec(cid, shape):
+    """ks_jacobian (OrbitKS.jacobian, ks/orbits.py:557-657): column j = J(u) e_j.  At 32x32 the one-orbit-per-warp kernel builds
+    the unit vectors itself (Jacobian mode) and reads orbit e / ncol for evaluation e; other sizes go through a stored identity.
+    Checked against the oracle's matvec on unit vectors -- a sample of columns at 32x32, all of them on the small grids."""
+    n, m = shape
+    B = 2
+    M, p, _, _ = _inputs(cid, n, m, B)
+    for cons in (ko.default_constraints(cid), (True, False, True)):
+        cmask = sum(1 << i for i in range(3) if cons[i]) | (0 if cid == 1 else 4)
+        Jt = E.jacobian(cid, n, m, M, p, cmask)
+        nm = M.shape[1] * M.shape[2]
+        free = [i for i in range(3) if not (cmask >> i) & 1]
+        assert Jt.shape == (B, nm + len(free), nm)
+        cols = range(nm + len(free)) if nm < 200 else list(range(0, nm, 41)) + list(range(nm - 3, nm + len(free)))
+        scale = max(np.max(np.abs(Jt)), 1.0)
+        for col in cols:
+            V = np.zeros((B, nm))
+            vp = np.zeros((B, 3))
+            if col < nm:
+                V[:, col] = 1.0
+            else:
+                vp[:, free[col - nm]] = 1.0
+            ref = ko.matvec(M, p, V.reshape(M.shape), vp, cid, tuple(bool((cmask >> i) & 1) for i in range(3)))
+            assert np.max(np.abs(Jt[:, col, :] - ref.reshape(B, nm))) < _tol(n, m) * scale, col

@@ -263,3 +263,103 @@ def test_empty_and_single_orbit_batches(cid, shape):
     assert torch.equal(one.matvec(one).state[0], big.matvec(big).state[2])
     rb, r1 = hunt(big, "adj", maxiter=25), hunt(one, "adj", maxiter=25)
     assert int(r1.status[0]) == int(rb.status[2]) and int(r1.nit[0]) == int(rb.nit[2]) and torch.equal(r1.orbit.state[0], rb.orbit.state[2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid", range(4))
+def test_warp32x1_matvec_rmatvec_vs_oracle_and_variant3(cid):
+    """matvec / rmatvec on the one-orbit-per-warp kernel (variant 4, the default) against the oracle and against the
+    two-orbits-per-warp kernel (variant 3), on a batch spanning several rounds of the persistent warps."""
+    from orbithunter_b200 import _lib
+    from oracle import ks_oracle as ko
+    from test_gpu_parity import _b
+
+    B = 2 * 148 * 8 + 53
+    rng = np.random.RandomState(10 + cid)
+    M = np.stack([ko.populate_state(44.0, 33.4, 32, 32, s % 61, cid) for s in range(B)]) * (1.0 + 1e-3 * np.arange(B)[:, None, None])
+    p = np.stack([44.0 + rng.rand(B), 33.4 + rng.rand(B), (rng.randn(B) if cid == 1 else np.zeros(B))], axis=1)
+    V = rng.randn(*M.shape) * (M != 0)
+    vp = rng.randn(B, 3)
+    L = _lib.lib()
+    out = {}
+    try:
+        for cons in (ko.default_constraints(cid), (True, False, True)):
+            for variant in (4, 3):
+                L.ks_debug_warp32_variant(variant)
+                u, vb = _b(cid, M, p, cons), _b(cid, V, vp, cons)
+                mv = u.matvec(vb).state.cpu().numpy()
+                r = u.rmatvec(vb)
+                out[variant] = (mv, r.state.cpu().numpy(), r.parameters.cpu().numpy())
+            omv = ko.matvec(M, p, V, vp, cid, cons)
+            ors, orp = ko.rmatvec(M, p, V, cid, cons)
+            for variant in (4, 3):
+                mv, rs, rp = out[variant]
+                assert np.max(np.abs(mv - omv)) < 1e-12 * np.max(np.abs(omv))
+                assert np.max(np.abs(rs - ors)) < 1e-12 * np.max(np.abs(ors))
+                assert np.allclose(rp, orp, rtol=1e-10, atol=1e-10 * np.max(np.abs(orp)) + 1e-300)
+            assert np.max(np.abs(out[4][0] - out[3][0])) < 1e-13 * np.max(np.abs(omv))
+    finally:
+        L.ks_debug_warp32_variant(4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid,shape", [(0, (32, 32)), (1, (32, 32)), (2, (32, 32)), (3, (32, 32)), (1, (16, 16)), (0, (64, 64))])
+def test_batched_jacobian_equals_matvec_on_unit_vectors(cid, shape):
+    """BatchedOrbitKS.jacobian (ks_jacobian; OrbitKS.jacobian ks/orbits.py:557-657): 32x32 uses the Jacobian mode of the
+    one-orbit-per-warp kernel, other sizes a stored identity.  J @ v must equal matvec(v) for random v (oracle), and a sample
+    of columns must equal the oracle's matvec on unit vectors."""
+    from oracle import ks_oracle as ko
+    from test_gpu_parity import _b
+
+    n, m = shape
+    B = 3 if n == 32 else 1
+    rng = np.random.RandomState(cid)
+    M = np.stack([ko.populate_state(44.0, 44.0, n, m, 5 + s, cid) for s in range(B)])
+    p = np.stack([44.0 + rng.rand(B), 44.0 + rng.rand(B), (rng.randn(B) if cid == 1 else np.zeros(B))], axis=1)
+    for cons in (ko.default_constraints(cid), (False, True, True)):
+        u = _b(cid, M, p, cons)
+        J = u.jacobian().cpu().numpy()
+        nm = M.shape[1] * M.shape[2]
+        free = [i for i in range(3) if not cons[i] and (i < 2 or cid == 1)]
+        assert J.shape == (B, nm, nm + len(free))
+        v = rng.randn(B, nm + len(free))
+        V = v[:, :nm].reshape(M.shape)
+        vp = np.zeros((B, 3))
+        for k, i in enumerate(free):
+            vp[:, i] = v[:, nm + k]
+        ref = ko.matvec(M, p, V, vp, cid, cons).reshape(B, nm)
+        got = np.einsum("bij,bj->bi", J, v)
+        assert np.max(np.abs(got - ref)) < 1e-11 * np.max(np.abs(ref))
+        for col in list(range(0, nm, max(1, nm // 7))) + list(range(nm, nm + len(free))):
+            e = np.zeros((B, nm + len(free)))
+            e[:, col] = 1.0
+            ep = np.zeros((B, 3))
+            for k, i in enumerate(free):
+                ep[:, i] = e[:, nm + k]
+            refc = ko.matvec(M, p, e[:, :nm].reshape(M.shape), ep, cid, cons).reshape(B, nm)
+            assert np.max(np.abs(J[:, :, col] - refc)) < 1e-12 * max(np.max(np.abs(J)), 1.0), col
+
+
+@pytest.mark.gpu
+def test_dense_newton_jacobian_mode_changes_no_result():
+    """hunt('lstsq') at 32x32 with the Jacobian built by the kernel's Jacobian mode (default) and by the batched matvec over a
+    stored identity.  The two Jacobians differ in the last bits (different summation order), and Newton far from an orbit
+    amplifies that, so: the converged orbits are converged either way and at least 90 % of the statuses agree."""
+    from orbithunter_b200 import BatchedOrbitKS, _lib
+    from orbithunter_b200.optimize import hunt
+
+    L = _lib.lib()
+    u = BatchedOrbitKS.from_seeds(np.arange(96), (44.0, 44.0, 0.0), "OrbitKS", (32, 32))
+    w = hunt(u, "adj", maxiter=2000).orbit
+    res = {}
+    try:
+        for on in (1, 0):
+            L.ks_debug_dense_jacobian_mode(on)
+            res[on] = hunt(w, "lstsq", maxiter=20, tol=1e-10)
+    finally:
+        L.ks_debug_dense_jacobian_mode(1)
+    a, b = res[1], res[0]
+    assert (a.status == b.status).float().mean().item() >= 0.9
+    ca, cb = a.costs[-1].cpu().numpy(), b.costs[-1].cpu().numpy()
+    conv = (a.status == 1).cpu().numpy()
+    assert conv.sum() > 0 and np.all(ca[conv] <= 1e-10) and np.all(cb[conv] <= 1e-10)
