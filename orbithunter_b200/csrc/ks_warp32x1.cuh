@@ -28,7 +28,7 @@ constexpr int kWarpsPerCta = KS_X1_WARPS_PER_CTA;  // tuning build: 4 -> two CTA
 #else
 constexpr int kWarpsPerCta = 8;
 #endif
-constexpr int kCtasPerSm = 8 / kWarpsPerCta;
+constexpr int kCtasPerSm = kWarpsPerCta >= 8 ? 1 : 8 / kWarpsPerCta;
 constexpr int kTileDoubles = 32 * 15 * 2;  // XB tile of one orbit: 480 double2
 constexpr int kPackedDoubles = 16 * 32 * 2;  // per orbit, packed lane-major layout of the fused adjoint pass (below)
 constexpr int kStageDoubles = 31 * 32;      // cp.async landing zone for the next orbit's half tuples (lane-private slots)

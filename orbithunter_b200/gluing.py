@@ -24,7 +24,8 @@ import torch
 
 from .batch import BatchedOrbitKS
 
-__all__ = ["aspect_ratio_correction", "glue", "tile", "glue_batch", "tile_batch", "rediscretize_tileset", "generate_symbol_arrays"]
+__all__ = ["aspect_ratio_correction", "glue", "tile", "glue_batch", "tile_batch", "rediscretize_tileset", "generate_symbol_arrays",
+           "pairwise_group_orbit", "expensive_pairwise_glue"]
 
 
 class _Patch:
@@ -303,3 +304,100 @@ def generate_symbol_arrays(tiling_dictionary, glue_shape, unique=True):
             out.append(arr)
         seen |= images
     return out
+
+
+# ---- pairwise search over group orbits (reference gluing.py:395-496) -----------------------------------------------------
+def pairwise_group_orbit(orbit_pair, **kwargs):
+    """All pairs of members of the two group orbits (reference gluing.py:395-421), first orbit's members in the outer loop."""
+    pair = np.asarray(orbit_pair, dtype=object).ravel()
+    yield from itertools.product(pair[0].group_orbit(**kwargs), pair[1].group_orbit(**kwargs))
+
+
+def _group_fields(orbit, kwargs):
+    """The fields of ``orbit.group_orbit(**kwargs)`` as one device tensor [G, n, m], in the generator's order, and the sign
+    each member's spatial shift carries (reflections negate it; ks/orbits.py:1143-1170, :1355-1401)."""
+    if kwargs.get("fundamental_domain", False):
+        raise NotImplementedError("expensive_pairwise_glue(fundamental_domain=True) is not provided")
+    field = orbit.transform(to="field")
+    F = torch.as_tensor(np.ascontiguousarray(field.state, dtype=np.float64)).cuda()
+    n, m = F.shape
+
+    def reflect(X):
+        return -torch.roll(torch.flip(X, dims=(-1,)), 1, dims=-1)
+
+    if kwargs.get("discrete", False):
+        half = torch.roll(F, m // 2, dims=1)
+        members, signs = [], []
+        for g, sgn in ((F, 1.0), (reflect(F), -1.0), (half, 1.0), (reflect(half), -1.0)):
+            members += [g, torch.roll(g, n // 2, dims=0)]
+            signs += [sgn, sgn]
+        return torch.stack(members), torch.tensor(signs, dtype=torch.float64, device=F.device)
+    r0, r1 = kwargs.get("rolls", (1, 1))
+    bases = [(F, 1.0)] if kwargs.get("continuous", False) else [(F, 1.0), (reflect(F), -1.0)]
+    Ns = torch.arange(0, n, r0, device=F.device)
+    Ms = torch.arange(0, m, r1, device=F.device)
+    rows = (torch.arange(n, device=F.device)[None, :] - Ns[:, None]) % n  # np.roll(a, N)[i] = a[(i - N) mod n]
+    cols = (torch.arange(m, device=F.device)[None, :] - Ms[:, None]) % m
+    out, signs = [], []
+    for g, sgn in bases:
+        out.append(g[rows[:, None, :, None], cols[None, :, None, :]].reshape(-1, n, m))
+        signs.append(torch.full((Ns.numel() * Ms.numel(),), sgn, dtype=torch.float64, device=F.device))
+    return torch.cat(out), torch.cat(signs)
+
+
+def expensive_pairwise_glue(orbit_pair, objective="cost", axis=0, **kwargs):
+    """Search every pair of group-orbit members of two orbits for the best join along ``axis`` (reference gluing.py:424-496).
+
+    The reference builds and scores one combination at a time; here the group orbits become two device tensors (rolls and
+    reflections as one gather each), and the combinations are joined, transformed and scored ``chunk`` (kwarg, default 8192)
+    at a time by the batched transform and eqn kernels.  ``objective``: "cost" -- 1/2 |F|^2 of the joined orbit -- or
+    "boundary_cost" -- the L2 distance of the rows / columns that meet (both seams when the axis is periodic); the reference
+    raises AttributeError for the latter (gluing.py:466 calls ``periodic_dimension``, which does not exist), the evident
+    intent is implemented.  Ties go to the first combination in the reference's iteration order, as its strict ``<`` does.
+    Group-orbit kwargs: ``rolls``, ``continuous``, ``discrete`` (ks/orbits.py:1355-1401); ``return_type``."""
+    pair = np.asarray(orbit_pair, dtype=object).ravel()
+    a, b = pair[0], pair[1]
+    return_type = kwargs.get("return_type", type(a))
+    chunk = int(kwargs.get("chunk", 8192))
+    GA, sa = _group_fields(a, kwargs)
+    GB, _ = _group_fields(b, kwargs)
+    if GA.shape[2 - axis] != GB.shape[2 - axis]:
+        raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
+    ta, xa, s0 = (a.parameters + (0.0,) * 3)[:3]
+    tb, xb = b.parameters[:2]
+    dims = tuple((2 if i == axis else 1) * 0.5 * (p + q) for i, (p, q) in enumerate(((ta, tb), (xa, xb))))
+    periodic = a.periodic_dimensions()[axis]
+    sr_roll = GB.shape[2] // 2 if (return_type._cls_name == "ShiftReflectionOrbitKS" and axis == 1) else 0
+    nb_members = GB.shape[0]
+    total = GA.shape[0] * nb_members
+    best_cost, best_idx = float("inf"), -1
+    for c0 in range(0, total, chunk):
+        idx = torch.arange(c0, min(c0 + chunk, total), device=GA.device)
+        ia, ib = idx // nb_members, idx % nb_members
+        if objective == "boundary_cost":
+            A, B = GA[ia], GB[ib]
+            if axis == 0:
+                d = (A[:, -1, :] - B[:, 0, :]).square().sum(1)
+                if periodic:
+                    d = d + (A[:, 0, :] - B[:, -1, :]).square().sum(1)
+            else:
+                d = (A[:, :, -1] - B[:, :, 0]).square().sum(1)
+                if periodic:
+                    d = d + (A[:, :, 0] - B[:, :, -1]).square().sum(1)
+            cost = d.sqrt()
+        else:
+            glued = torch.cat((GA[ia], GB[ib]), dim=1 + axis)
+            if sr_roll:
+                glued = torch.roll(glued, sr_roll, dims=2)
+            params = torch.stack((torch.full_like(sa[ia], dims[0]), torch.full_like(sa[ia], dims[1]), sa[ia] * s0), dim=1)
+            cost = BatchedOrbitKS(glued, params, return_type._cls_name, "field").transform("modes").cost()
+        cmin = float(cost.min())
+        if cmin < best_cost:
+            best_cost, best_idx = cmin, c0 + int((cost == cmin).nonzero()[0])
+    ia, ib = best_idx // nb_members, best_idx % nb_members
+    fa = a.transform(to="field")
+    fb = b.transform(to="field")
+    ga = fa._new(state=GA[ia].cpu().numpy(), parameters=(ta, xa, float(sa[ia]) * s0))
+    gb = fb._new(state=GB[ib].cpu().numpy())
+    joined = ga.concat(gb, axis=axis)
+    return return_type(**vars(joined)).transform(to=a.basis)

@@ -18,7 +18,7 @@ import time
 
 import numpy as np
 
-__all__ = ["to_h5", "to_h5_batch", "read_h5", "h5_tree"]
+__all__ = ["to_h5", "to_h5_batch", "read_h5", "h5_tree", "read_tileset", "to_symbol_string", "to_symbol_array"]
 
 _UNDEF = 0xFFFFFFFFFFFFFFFF
 _SIGNATURE = b"\x89HDF\r\n\x1a\n"
@@ -457,3 +457,28 @@ def read_h5(filename, *datanames, validate=False, **orbitkwargs):
     if validate:
         return [x.preprocess() for x in imported]
     return imported
+
+
+def read_tileset(filename, keys, orbit_names, validate=False, **orbitkwargs):
+    """io.read_tileset (io.py:142-169): the tiling dictionary {key: orbit} for ``gluing.tile`` from datasets of one file."""
+    if len(keys) != len(orbit_names):
+        raise AssertionError("as many keys as orbit names are needed")
+    orbits = read_h5(filename, tuple(orbit_names), validate=validate, **orbitkwargs)
+    return dict(zip(keys, orbits if isinstance(orbits, list) else [orbits]))
+
+
+def to_symbol_string(symbol_array):
+    """io.to_symbol_string (io.py:172-181): the symbols of an array as one string -- [[0, 1], [2, 0]] -> "01_20".  Pass k
+    (k = 0, 1, ...) groups the current pieces in runs of ``shape[1 + k]`` and joins each run with k underscores; what is left
+    is joined with ``ndim - 1`` underscores.  (Same grouping as the reference, including for arrays whose trailing axes have
+    different lengths.)"""
+    arr = np.asarray(symbol_array)
+    pieces = [str(v) for v in arr.ravel().tolist()]
+    for k, run in enumerate(arr.shape[1:]):
+        pieces = [("_" * k).join(pieces[p:p + run]) for p in range(0, len(pieces), run)]
+    return ("_" * (arr.ndim - 1)).join(pieces)
+
+
+def to_symbol_array(symbol_string, symbol_array_shape):
+    """io.to_symbol_array (io.py:184-189): inverse of ``to_symbol_string`` for single-digit symbols."""
+    return np.array([ch for ch in symbol_string.replace("_", "")]).astype(int).reshape(symbol_array_shape)

@@ -579,6 +579,65 @@ class OrbitKS:
         out.equilibrium = True
         return out
 
+    # ---- symmetry operations and joining (ks/orbits.py:1143-1232, :1355-1401; core.py:1282-1380) ------------------------
+    def roll(self, shift, axis=0):
+        """np.roll of the field along ``axis`` (ks/orbits.py:1172-1194), returned in the basis of self.  (For a field-basis
+        orbit this is the reference's result; for other bases the reference relabels the rolled field with the old basis.)"""
+        f = self.transform(to="field")
+        return f._new(state=np.roll(f.state, shift, axis=axis)).transform(to=self.basis)
+
+    def cell_shift(self, n_cell, axis=0):
+        """Rotation by 1 / n_cell of the domain along ``axis``, to the nearest grid point (ks/orbits.py:1196-1232)."""
+        shift = np.sign(n_cell) * np.array(self.discretization)[np.array(axis)] // np.abs(n_cell)
+        return self.roll(shift, axis=axis)
+
+    def reflection(self, axis=1, signed=True):
+        """-u(L - x, t) (ks/orbits.py:1143-1170): flip the columns, roll by one along ``axis`` (the reflection axis sits on a
+        grid point), negate; the spatial shift changes sign."""
+        f = self.transform(to="field")
+        t, x, sft = self.parameters
+        return f._new(state=-1.0 * np.roll(np.fliplr(f.state), 1, axis=axis), parameters=(t, x, -1 * sft)).transform(to=self.basis)
+
+    def to_fundamental_domain(self, **kwargs):
+        return self  # core.py: no discrete symmetry, the whole tile
+
+    def from_fundamental_domain(self, **kwargs):
+        return self
+
+    def concat(self, other, axis=0):
+        """Join two orbits (core.py:1282-1380): states concatenated along ``axis`` as they are (the bases are not checked),
+        the dimension along ``axis`` summed and the other averaged (glue_dimensions, core.py:899-945), the remaining
+        parameters those of self, discretization re-read from the new state."""
+        state = np.concatenate((self.state, other.state), axis=axis)
+        if self.parameters is not None and other.parameters is not None:
+            dims = tuple((2 if i == axis else 1) * 0.5 * (self.parameters[i] + other.parameters[i]) for i in range(2))
+        elif self.parameters is not None or other.parameters is not None:
+            src = self if self.parameters is not None else other
+            dims = tuple(float(d) * (new / old) if new > 1 else 0.0 for d, new, old in zip(src.parameters[:2], state.shape, src.shape))
+        else:
+            return self._new(state=state, discretization=None)
+        base = self.parameters if self.parameters is not None else other.parameters
+        return self._new(state=state, parameters=dims + tuple(base[2:]), discretization=None)
+
+    def group_orbit(self, **kwargs):
+        """Generator over the group orbit (ks/orbits.py:1355-1401): ``discrete=True`` -- {1, reflection, half-cell shift in
+        space, both} x {1, half-cell shift in time}; ``continuous=True`` -- all rolls by multiples of ``rolls``; default --
+        those rolls of the orbit and of its reflection."""
+        fd = kwargs.get("fundamental_domain", False)
+        if kwargs.get("discrete", False):
+            half = self.cell_shift(2, axis=1)
+            for g_space in (self, self.reflection(), half, half.reflection()):
+                for g in (g_space, g_space.cell_shift(2, axis=0)):
+                    yield g.to_fundamental_domain() if fd else g
+            return
+        rolls = kwargs.get("rolls", (1, 1))
+        for g in ((self,) if kwargs.get("continuous", False) else (self, self.reflection())):
+            for N in range(0, g.n, rolls[0]):
+                for M in range(0, g.m, rolls[1]):
+                    r = g.roll(N, axis=0).roll(M, axis=1)
+                    yield r.to_fundamental_domain() if fd else r
+
+
 class RelativeOrbitKS(OrbitKS):
     _cls_name = "RelativeOrbitKS"
 
@@ -628,12 +687,26 @@ class _HalfColumnMixin:
         return shape[0] + 1, 2 * shape[1] + 2
 
 
+def _no_fundamental_domain(self, *args, **kwargs):
+    raise NotImplementedError("fundamental-domain slicing (ks/orbits.py:3229-3252, :3688-3711, :3010-3014) is not provided")
+
+
+RelativeOrbitKS.to_fundamental_domain = RelativeOrbitKS.from_fundamental_domain = _no_fundamental_domain
+
+
 class ShiftReflectionOrbitKS(_HalfColumnMixin, OrbitKS):
     _cls_name = "ShiftReflectionOrbitKS"
+    to_fundamental_domain = from_fundamental_domain = _no_fundamental_domain
+
+    def concat(self, other, axis=0):
+        """ks/orbits.py:3640-3676: joined in space, the result is rolled by half of the second tile's width."""
+        joined = super().concat(other, axis=axis)
+        return joined.roll(other.m // 2, axis=1) if axis == 1 else joined
 
 
 class AntisymmetricOrbitKS(_HalfColumnMixin, OrbitKS):
     _cls_name = "AntisymmetricOrbitKS"
+    to_fundamental_domain = from_fundamental_domain = _no_fundamental_domain
 
     @staticmethod
     def _default_shape():

@@ -68,3 +68,26 @@ def test_reads_the_reference_fixture_written_by_h5py():
         a2, at2 = ours[group][name]
         assert np.array_equal(arr, a2) and at2["class"] == attrs["class"] and at2["basis"] == attrs["basis"]
         assert np.array_equal(at2["parameters"], attrs["parameters"]) and list(at2["discretization"]) == list(attrs["discretization"])
+
+
+def test_symbol_strings_follow_the_reference_grouping():
+    """io.to_symbol_string / to_symbol_array (io.py:172-189); expected strings are outputs of the reference."""
+    from orbithunter_b200.h5io import to_symbol_array, to_symbol_string
+
+    cases = [(np.array([[0, 1], [2, 0]]), "01_20"), (np.arange(8).reshape(2, 2, 2) % 3, "01_20__12_01"), (np.array([1, 2, 0]), "120"),
+             (np.arange(24).reshape(2, 3, 4) % 5, "012_340_123_401__234_012_340_123"), (np.arange(6).reshape(3, 2), "01_23_45")]
+    for arr, want in cases:
+        assert to_symbol_string(arr) == want
+        assert np.array_equal(to_symbol_array(want, arr.shape), arr)
+
+
+def test_read_tileset_builds_the_tiling_dictionary(tmp_path):
+    """io.read_tileset (io.py:142-169): {key: orbit} in the order of the names given."""
+    f = str(tmp_path / "tiles.h5")
+    tree = {"streak": {"0": _leaf(0)}, "defect": {"0": _leaf(1, "RelativeOrbitKS")}, "wiggle": {"0": _leaf(2, "AntisymmetricOrbitKS", (3, 2))}}
+    h5io.write_tree(f, tree)
+    tiles = h5io.read_tileset(f, (0, 1, 2), ("streak", "wiggle", "defect"))
+    assert [type(tiles[k]).__name__ for k in (0, 1, 2)] == ["OrbitKS", "AntisymmetricOrbitKS", "RelativeOrbitKS"]
+    assert np.array_equal(tiles[1].state, tree["wiggle"]["0"][0]) and tiles[2].parameters == (2.5, 2.5, 0.25)
+    with pytest.raises(AssertionError):
+        h5io.read_tileset(f, (0, 1), ("streak",))
