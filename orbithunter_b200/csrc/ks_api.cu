@@ -894,7 +894,10 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
     return cudaGetLastError() == cudaSuccess ? 0 : fail(KS_ERR_LAUNCH, "dense Newton step: kernel launch failed");
   };
 
-  // initial cost and loop mask
+  // initial cost and loop mask.  The line search evaluates the whole batch at (tu, tup) every step: slots of orbits that are
+  // never live keep this copy of their orbit instead of uninitialised workspace
+  KS_CHECK_CUDA(cudaMemcpyAsync(tu, modes, (size_t)batch * nm * 8, cudaMemcpyDeviceToDevice, s), "solver driver setup");
+  KS_CHECK_CUDA(cudaMemcpyAsync(tup, params, (size_t)batch * 24, cudaMemcpyDeviceToDevice, s), "solver driver setup");
   int rc = eval_eqn(modes, params, Fy, cost_out);
   if (rc != 0) return rc;
   KS_LAUNCH(nk_init_kernel, (batch + 255) / 256, 256, 0, s, status_out, nit_out, live, searching, cost_out, tol, batch);
