@@ -658,7 +658,7 @@ def main():
         line["config2"] = config2_block(peak)
         line["config3"] = config3_block(peak)
         line["other_shapes"] = side_shapes(peak)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU leg runs on rank 0 at N = 1 only
         if reference_available():
             rate, n_done = reference_evals_per_s(16, 10.0, 1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference",
