@@ -151,6 +151,10 @@ __global__ void __launch_bounds__(kThreads) chol_diag_kernel(const double* G, do
 
 // y = L^-T L^-1 r for one orbit per CTA.  Lf holds L (column-major, ld nm), Li the inverted diagonal blocks.  r is read from
 // `rhs`, y written to `y` (both [C][nm]); the vector lives in shared memory, L is streamed once per direction.
+// The panel updates are the HBM traffic of the kernel.  Forward, a thread owns two adjacent rows (one 16-byte load per column,
+// two columns in flight per step); backward, eight lanes share a column (the 64 rows of the block are 512 contiguous bytes:
+// four 16-byte loads per lane, then a three-step shuffle reduction), four columns per warp.  Both need 16-byte alignment, i.e.
+// an even nm; odd nm (ShiftReflection / Antisymmetric grids with odd mode counts) takes the scalar loops.
 __global__ void __launch_bounds__(kThreads) tri_solve_kernel(const double* Lf, const double* Li, const double* rhs, double* y, int nm) {
   KS_DYN_SMEM(double, vec);  // nm doubles + kNb
   double* zk = vec + nm;
@@ -158,6 +162,7 @@ __global__ void __launch_bounds__(kThreads) tri_solve_kernel(const double* Lf, c
   const double* L = Lf + (size_t)c * nm * nm;
   const int nblk = (nm + kNb - 1) / kNb;
   const double* li0 = Li + (size_t)c * nblk * kNb * kNb;
+  const bool vec2 = (nm & 1) == 0;
   for (int i = threadIdx.x; i < nm; i += blockDim.x) vec[i] = rhs[(size_t)c * nm + i];
   __syncthreads();
   // forward: z_k = Li_k v_k;  v[k1:] -= L[k1:, k0:k1] z_k
@@ -172,10 +177,28 @@ __global__ void __launch_bounds__(kThreads) tri_solve_kernel(const double* Lf, c
     }
     __syncthreads();
     if (threadIdx.x < b) vec[k0 + threadIdx.x] = zk[threadIdx.x];
-    for (int i = k1 + threadIdx.x; i < nm; i += blockDim.x) {
-      double s = 0.0;
-      for (int j = 0; j < b; ++j) s = fma(L[(size_t)(k0 + j) * nm + i], zk[j], s);
-      vec[i] -= s;
+    if (vec2 && b == kNb) {  // (rows exist below the block only when it is a full one)
+      for (int i = k1 + 2 * threadIdx.x; i < nm; i += 2 * blockDim.x) {
+        const double* p = L + (size_t)k0 * nm + i;
+        double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+#pragma unroll 8
+        for (int j = 0; j < kNb; j += 2) {
+          const double2 a0 = *reinterpret_cast<const double2*>(p + (size_t)j * nm);
+          const double2 a1 = *reinterpret_cast<const double2*>(p + (size_t)(j + 1) * nm);
+          s0 = fma(a0.x, zk[j], s0);
+          s1 = fma(a0.y, zk[j], s1);
+          t0 = fma(a1.x, zk[j + 1], t0);
+          t1 = fma(a1.y, zk[j + 1], t1);
+        }
+        vec[i] -= s0 + t0;
+        vec[i + 1] -= s1 + t1;
+      }
+    } else {
+      for (int i = k1 + threadIdx.x; i < nm; i += blockDim.x) {
+        double s = 0.0;
+        for (int j = 0; j < b; ++j) s = fma(L[(size_t)(k0 + j) * nm + i], zk[j], s);
+        vec[i] -= s;
+      }
     }
     __syncthreads();
   }
@@ -191,11 +214,40 @@ __global__ void __launch_bounds__(kThreads) tri_solve_kernel(const double* Lf, c
     }
     __syncthreads();
     if (threadIdx.x < b) vec[k0 + threadIdx.x] = zk[threadIdx.x];
-    for (int j = threadIdx.x; j < k0; j += blockDim.x) {
-      const double* col = L + (size_t)j * nm + k0;
-      double s = 0.0;
-      for (int r = 0; r < b; ++r) s = fma(col[r], zk[r], s);
-      vec[j] -= s;
+    if (vec2) {
+      if (threadIdx.x >= b && threadIdx.x < kNb) zk[threadIdx.x] = 0.0;  // a short last block: pad the multiplier with zeros
+      __syncthreads();
+      const int l8 = threadIdx.x & 7, r0 = 8 * l8;
+      // rows k0 + r0 .. + 7 of a column; past the end of a short block the multiplier is zero and the load is skipped
+      double z[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) z[e] = zk[r0 + e];
+      // warp-uniform trip count (the shuffles below name the whole warp); k0 is a multiple of 64, so j < k0 for every group
+      for (int jw = (threadIdx.x >> 5) * 4; jw < k0; jw += (blockDim.x >> 5) * 4) {
+        const int j = jw + ((threadIdx.x & 31) >> 3);
+        const double* col = L + (size_t)j * nm + k0 + r0;
+        double s = 0.0, t = 0.0;
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          if (j < k0 && r0 + e < b) {  // b is even when nm is: pairs never straddle the end
+            const double2 a = *reinterpret_cast<const double2*>(col + e);
+            s = fma(a.x, z[e], s);
+            t = fma(a.y, z[e + 1], t);
+          }
+        }
+        s += t;
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (l8 == 0 && j < k0) vec[j] -= s;
+      }
+    } else {
+      for (int j = threadIdx.x; j < k0; j += blockDim.x) {
+        const double* col = L + (size_t)j * nm + k0;
+        double s = 0.0;
+        for (int r = 0; r < b; ++r) s = fma(col[r], zk[r], s);
+        vec[j] -= s;
+      }
     }
     __syncthreads();
   }
