@@ -172,3 +172,22 @@ def test_operator_cache_of_the_64x64_krylov_driver_changes_no_bit(cid, method):
     rm, rp, st = ko.newton_krylov(M[0], p[0], cid, method="gmres" if method == 0 else "lsqr", maxiter=1,
                                   scipy_kwargs=dict(restart=3, maxiter=1) if method == 0 else dict(iter_lim=4))
     assert abs(out[1][4][0] - st["cost"]) <= 1e-9 * st["cost"] and relerr(out[1][0][0], rm) < 1e-9
+
+
+@pytest.mark.parametrize("cid", [0, 1])
+def test_lsqr_at_32x32_runs_matvec_and_rmatvec_on_the_one_orbit_per_warp_kernel(cid):
+    """32x32 Newton-LSQR: the operator applications go through ks_warp32x1_kernel<MATVEC / RMATVEC> with the cdof layouts of the
+    Krylov driver (v and the free parameters in one vector of stride N, results likewise) -- against the SciPy-based oracle."""
+    n = m = 32
+    B = 3  # more orbits than one round of the emulated grid's first warps; odd
+    M = np.stack([ko.populate_state(44.0, 44.0, n, m, 3 + s, cid) for s in range(B)])
+    p = np.tile([44.0, 44.0, 0.3 if cid == 1 else 0.0], (B, 1))
+    cons = ko.default_constraints(cid)
+    cmask = sum(1 << i for i in range(3) if cons[i])
+    Mo, po, status, nit, cost, cnt = E.newton_krylov(cid, n, m, M, p, cmask, 1, maxiter=1, inner=4, atol=1e-6, btol=1e-6)
+    for b in range(B):
+        rm, rp, st = ko.newton_krylov(M[b], p[b], cid, method="lsqr", maxiter=1, scipy_kwargs=dict(iter_lim=4))
+        assert (int(status[b]), int(nit[b])) == (st["status"], st["nit"])
+        assert abs(cost[b] - st["cost"]) <= 1e-9 * max(1.0, st["cost"])
+        assert relerr(Mo[b], rm) < 1e-8 and np.allclose(po[b], rp, rtol=1e-8)
+    assert cnt[0] > 0
