@@ -46,6 +46,9 @@ void ks_debug_warp32_variant(int variant);
 /* tuning hook, dense Newton step at 32x32: 1 (default) = Jacobian columns by the one-orbit-per-warp kernel's Jacobian mode
  * (unit vectors made in the kernel, orbit read in place); 0 = batched matvec over a stored identity and replicated orbits. */
 void ks_debug_dense_jacobian_mode(int on);
+/* tuning hook, dense Newton step: Cholesky blocks (of 64) per outer panel of the two-level factorisation; 4 (default) updates
+ * the matrix to the right of a panel with rank 256 at once, 1 with rank 64 after every block. */
+void ks_debug_dense_outer_blocks(int blocks);
 /* tuning hook, 32x32 kernels: nanoseconds between the start of the warps that share one SM scheduler (default 0). */
 void ks_debug_warp32_stagger(int ns);
 /* tuning hook, 32x32 variant 6: 1 (default) = token passing between the two warp groups, 0 = free-running warps. */

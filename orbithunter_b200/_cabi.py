@@ -8,6 +8,7 @@ _SIG = {
     "ks_debug_force_generic": (None, [C.c_int]),
     "ks_debug_warp32_variant": (None, [C.c_int]),
     "ks_debug_dense_jacobian_mode": (None, [C.c_int]),
+    "ks_debug_dense_outer_blocks": (None, [C.c_int]),
     "ks_debug_warp32_stagger": (None, [C.c_int]),
     "ks_debug_warp32_pingpong": (None, [C.c_int]),
     "ks_debug_tile": (None, [C.c_int, C.c_int]),

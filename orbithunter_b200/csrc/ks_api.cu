@@ -32,6 +32,7 @@ int g_w32_stagger_ns = 0;  // tuning: start delay between the warps of one sched
 bool g_force_generic = false;  // debug/test switch: route 32x32 through the generic kernel as a cross-check
 int g_warp32_variant = 4;  // 32x32 kernels: 4 = one orbit per warp (ks_warp32x1.cuh, default), 3 = two orbits per warp (ks_warp32.cuh,
                            // which also serves matvec / rmatvec for variants 5, 6, 7)
+int g_dense_outer = 4;  // dense Newton step: Cholesky blocks per outer panel of the two-level factorisation (1: rank-64 updates throughout)
 int g_dense_jac_mode = 1;  // dense Newton step, 32x32: Jacobian columns by the x1 kernel's Jacobian mode (0: matvec over a stored identity)
 bool use_warp32(int n, int m) { return n == 32 && m == 32 && !g_force_generic; }
 int warp32_grid(int batch, int warps_per_cta) {
@@ -151,6 +152,7 @@ void ks_debug_tile(int enabled, int chunk_mb) {
 void ks_debug_warp32_pingpong(int mode) { g_w32_pingpong = mode; }
 void ks_debug_warp32_stagger(int ns) { g_w32_stagger_ns = ns < 0 ? 0 : ns; }
 void ks_debug_dense_jacobian_mode(int on) { g_dense_jac_mode = on ? 1 : 0; }
+void ks_debug_dense_outer_blocks(int blocks) { g_dense_outer = blocks >= 1 && blocks <= 64 ? blocks : 4; }
 void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant >= 3 && variant <= 7) ? variant : 4; }
 
 int ks_mode_size(int cls, int n, int m) { return shape_ok(cls, n, m) ? (n - 1) * mode_cols(cls, m) : 0; }
@@ -868,12 +870,24 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
             if ((rc_dense = ksdh::dgemm_batched(s, false, true, rest, b, b, 1.0, G + k1 + (size_t)k0 * nm, nm, sG,
                                                 Li + (size_t)blk * ksd::kNb * ksd::kNb, ksd::kNb, sLi, 0.0, Lf + k1 + (size_t)k0 * nm, nm, sG, C)) != 0)
               return rc_dense;
-            // lower triangle only, in column strips of 4 Cholesky blocks (each strip includes its diagonal square)
-            for (int c1s = k1; c1s < nm; c1s += 4 * ksd::kNb) {
-              const int wc = nm - c1s < 4 * ksd::kNb ? nm - c1s : 4 * ksd::kNb;
-              if ((rc_dense = ksdh::dgemm_batched(s, false, true, nm - c1s, wc, b, -1.0, Lf + c1s + (size_t)k0 * nm, nm, sG,
-                                                  Lf + c1s + (size_t)k0 * nm, nm, sG, 1.0, G + c1s + (size_t)c1s * nm, nm, sG, C)) != 0)
+            // Two-level blocking: inside an outer panel of `outer` Cholesky blocks only the panel's own columns are updated after
+            // each block (rank 64); the columns to its right get the whole panel's contribution at once (rank 64 * outer), in
+            // column strips of 4 blocks, lower triangle only (each strip includes its diagonal square).  Rank-64 updates of the
+            // whole trailing matrix ran at 15 TFLOP/s, the rank-256 ones run at the rate of the J J^T products.
+            const int outer = g_dense_outer;
+            const int K0 = (blk / outer) * outer * ksd::kNb;
+            const int K1 = K0 + outer * ksd::kNb < nm ? K0 + outer * ksd::kNb : nm;
+            if (K1 > k1) {
+              if ((rc_dense = ksdh::dgemm_batched(s, false, true, nm - k1, K1 - k1, b, -1.0, Lf + k1 + (size_t)k0 * nm, nm, sG,
+                                                  Lf + k1 + (size_t)k0 * nm, nm, sG, 1.0, G + k1 + (size_t)k1 * nm, nm, sG, C)) != 0)
                 return rc_dense;
+            } else {  // last block of the outer panel: everything to the right, rank K1 - K0
+              for (int c1s = K1; c1s < nm; c1s += 4 * ksd::kNb) {
+                const int wc = nm - c1s < 4 * ksd::kNb ? nm - c1s : 4 * ksd::kNb;
+                if ((rc_dense = ksdh::dgemm_batched(s, false, true, nm - c1s, wc, K1 - K0, -1.0, Lf + c1s + (size_t)K0 * nm, nm, sG,
+                                                    Lf + c1s + (size_t)K0 * nm, nm, sG, 1.0, G + c1s + (size_t)c1s * nm, nm, sG, C)) != 0)
+                  return rc_dense;
+              }
             }
           }
         }
