@@ -120,11 +120,13 @@ __global__ void __launch_bounds__(kThreads) chol_diag_kernel(const double* G, do
     const double r = sqrt(d), ir = 1.0 / r;
     for (int i = j + threadIdx.x; i < b; i += blockDim.x) A[j][i] = (i == j) ? r : A[j][i] * ir;
     __syncthreads();
-    // trailing update of the block: A[k][i] -= A[j][i] * A[j][k] for j < k <= i
-    const int t = b - j - 1;
-    for (int e = threadIdx.x; e < t * t; e += blockDim.x) {
-      const int kk = j + 1 + e / t, i = j + 1 + e % t;
-      if (i >= kk) A[kk][i] -= A[j][i] * A[j][kk];
+    // trailing update of the block: A[k][i] -= A[j][i] * A[j][k] for j < k <= i; thread = (row i, every fourth column k)
+    {
+      const int i = threadIdx.x & (kNb - 1);
+      if (i > j && i < b) {
+        const double aji = A[j][i];
+        for (int kk = j + 1 + (threadIdx.x >> 6); kk <= i; kk += kThreads / kNb) A[kk][i] -= aji * A[j][kk];
+      }
     }
     __syncthreads();
   }
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(kThreads) chol_diag_kernel(const double* G, do
     X[j][j] = 1.0 / A[j][j];
     for (int i = j + 1; i < b; ++i) {
       double s = 0.0;
+#pragma unroll 8
       for (int k = j; k < i; ++k) s = fma(A[k][i], X[j][k], s);
       X[j][i] = -s / A[i][i];
     }
