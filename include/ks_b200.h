@@ -43,9 +43,11 @@ void ks_debug_force_generic(int on);
  * 7 = variant 4 for eqn / costgrad, variant 3 for matvec / rmatvec (the default before the one-orbit-per-warp kernel
  * learned those two ops). */
 void ks_debug_warp32_variant(int variant);
-/* tuning hook, dense Newton step at 32x32: 1 (default) = Jacobian columns by the one-orbit-per-warp kernel's Jacobian mode
- * (unit vectors made in the kernel, orbit read in place); 0 = batched matvec over a stored identity and replicated orbits. */
-void ks_debug_dense_jacobian_mode(int on);
+/* tuning hook, dense Newton step at 32x32: 2 (default) = matrix-free -- J J^T column by column as J (J^T e_j) by two launches
+ * of the one-orbit-per-warp kernel, J^T y and J dx of the solve as single rmatvec / matvec launches, no Jacobian in memory;
+ * 1 = Jacobian by that kernel's Jacobian mode (unit vectors made in the kernel), J J^T by batched library GEMMs;
+ * 0 = Jacobian by a batched matvec over a stored identity and replicated orbits, J J^T by GEMMs (the path of other sizes). */
+void ks_debug_dense_jacobian_mode(int mode);
 /* tuning hook, dense Newton step: Cholesky blocks (of 64) per outer panel of the two-level factorisation; 4 (default) updates
  * the matrix to the right of a panel with rank 256 at once, 1 with rank 64 after every block. */
 void ks_debug_dense_outer_blocks(int blocks);

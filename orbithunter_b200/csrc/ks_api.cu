@@ -33,7 +33,8 @@ bool g_force_generic = false;  // debug/test switch: route 32x32 through the gen
 int g_warp32_variant = 4;  // 32x32 kernels: 4 = one orbit per warp (ks_warp32x1.cuh, default), 3 = two orbits per warp (ks_warp32.cuh,
                            // which also serves matvec / rmatvec for variants 5, 6, 7)
 int g_dense_outer = 4;  // dense Newton step: Cholesky blocks per outer panel of the two-level factorisation (1: rank-64 updates throughout)
-int g_dense_jac_mode = 1;  // dense Newton step, 32x32: Jacobian columns by the x1 kernel's Jacobian mode (0: matvec over a stored identity)
+int g_dense_jac_mode = 2;  // dense Newton step, 32x32: 2 = matrix-free J J^T (no Jacobian), 1 = Jacobian by the x1 kernel's Jacobian mode + GEMM,
+                           // 0 = Jacobian by a matvec over a stored identity + GEMM
 bool use_warp32(int n, int m) { return n == 32 && m == 32 && !g_force_generic; }
 int warp32_grid(int batch, int warps_per_cta) {
   const int npairs = (batch + 1) / 2;
@@ -151,7 +152,7 @@ void ks_debug_tile(int enabled, int chunk_mb) {
 }
 void ks_debug_warp32_pingpong(int mode) { g_w32_pingpong = mode; }
 void ks_debug_warp32_stagger(int ns) { g_w32_stagger_ns = ns < 0 ? 0 : ns; }
-void ks_debug_dense_jacobian_mode(int on) { g_dense_jac_mode = on ? 1 : 0; }
+void ks_debug_dense_jacobian_mode(int mode) { g_dense_jac_mode = (mode >= 0 && mode <= 2) ? mode : 2; }
 void ks_debug_dense_outer_blocks(int blocks) { g_dense_outer = blocks >= 1 && blocks <= 64 ? blocks : 4; }
 void ks_debug_warp32_variant(int variant) { g_warp32_variant = (variant >= 3 && variant <= 7) ? variant : 4; }
 
@@ -240,7 +241,7 @@ int ks_jacobian(int cls, int n, int m, int batch, const double* modes, const dou
   std::memset(&a, 0, sizeof(a));
   a.cmask = cmask;
   if (use_warp32(n, m)) {  // unit vectors made in the kernel, u read in place (ks_warp32x1.cuh, Jacobian mode)
-    a.modes = modes; a.params = params; a.out_state = jac_t; a.batch = batch * N; a.jac_ncol = N;
+    a.modes = modes; a.params = params; a.out_state = jac_t; a.batch = batch * N; a.u_div = N; a.unit_v = 1;
     return dispatch<KS_OP_MATVEC>(cls, n, m, a, ws, ws_bytes, stream);
   }
   double* Urep = static_cast<double*>(ws);
@@ -812,13 +813,24 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
       const int C = n_live - c0 < chunk ? n_live - c0 : chunk;
       const int* idx = d_idx + c0;
       KS_LAUNCH(ksd::gather_kernel, C, 256, 0, s, idx, (const double*)modes, (const double*)params, (const double*)Fy, Uc, Pc, rhs0, nm);
+      // 32x32, matrix-free (default): G = J J^T column by column as J (J^T e_j) -- two launches of the one-orbit-per-warp
+      // kernel (rmatvec over unit vectors made in the kernel, then matvec over the result) instead of a Jacobian and a
+      // 2 Nm^2 N flop product; the products J^T y and J dx of the solve are single matvec / rmatvec launches.
+      const bool mfree = use_warp32(n, m) && g_dense_jac_mode == 2;
+      if (mfree) {
+        KsEvalArgs a;  // W[c][j][:] = J^T e_j in the cdof layout; W lives where the Jacobian would
+        std::memset(&a, 0, sizeof(a));
+        a.modes = Uc; a.params = Pc; a.out_state = J; a.batch = C * nm; a.cmask = cmask; a.u_div = nm; a.unit_v = 1;
+        a.out_ld = N; a.out_tail = 1;
+        n_ops += nm;
+        if ((rc_dense = dispatch<KS_OP_RMATVEC>(cls, n, m, a, jws, jws_bytes, stream)) != 0) return rc_dense;
+      } else if (use_warp32(n, m) && g_dense_jac_mode) {
       // Jacobian: one batched matvec over the identity; column `col` of orbit c is evaluation number c * N + col
-      if (use_warp32(n, m) && g_dense_jac_mode) {
         // 32x32: the one-orbit-per-warp kernel builds the unit vectors itself and reads u / parameters of orbit c for
         // every column (no replicated copies, no identity in memory)
         KsEvalArgs a;
         std::memset(&a, 0, sizeof(a));
-        a.modes = Uc; a.params = Pc; a.out_state = J; a.batch = C * N; a.cmask = cmask; a.jac_ncol = N;
+        a.modes = Uc; a.params = Pc; a.out_state = J; a.batch = C * N; a.cmask = cmask; a.u_div = N; a.unit_v = 1;
         n_ops += N;
         if ((rc_dense = dispatch<KS_OP_MATVEC>(cls, n, m, a, jws, jws_bytes, stream)) != 0) return rc_dense;
       } else {
@@ -844,9 +856,16 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
             return fail(KS_ERR_LAUNCH, "dense Newton step: device error while checking the factorisation");
           if (n_redo == 0) break;
         }
+        if (mfree) {
+          KsEvalArgs a;  // column j of G = J w_j, w_j = row j of W
+          std::memset(&a, 0, sizeof(a));
+          a.modes = Uc; a.params = Pc; a.vmodes = J; a.v_ld = N; a.v_tail = 1; a.out_state = G; a.batch = C * nm; a.cmask = cmask;
+          a.u_div = nm;
+          n_ops += nm;
+          if ((rc_dense = dispatch<KS_OP_MATVEC>(cls, n, m, a, jws, jws_bytes, stream)) != 0) return rc_dense;
+        } else {
         // G = J J^T is symmetric and only its lower triangle is read below: block rows x block columns up to the diagonal
         // (an 8 x 8 partition does 36 of the 64 block products; measured 2 % faster than 4 x 4, finer is slower)
-        {
           static const int parts_env = std::getenv("KS_DENSE_PARTS") ? std::atoi(std::getenv("KS_DENSE_PARTS")) : 0;  // tuning
           const int parts = parts_env > 0 ? parts_env : (nm >= 512 ? 8 : (nm >= 128 ? 2 : 1));  // 8: 36 of 64 block products
           const int bs = (((nm + parts - 1) / parts) + ksd::kNb - 1) / ksd::kNb * ksd::kNb;  // multiple of the Cholesky block
@@ -896,12 +915,29 @@ int newton_driver(int cls, int n, int m, int batch, double* modes, double* param
       for (int it = 0; it <= refine; ++it) {
         const double* r = rhs0;
         if (it > 0) {
-          KS_LAUNCH(ksd::gemv_kernel, C, ksd::kThreads, x_smem, s, (const double*)J, (const double*)dxc, (const double*)rhs0, res, nm, N, 1, 0);
+          if (mfree) {  // res = rhs0 - J dx
+            KsEvalArgs a;
+            std::memset(&a, 0, sizeof(a));
+            a.modes = Uc; a.params = Pc; a.vmodes = dxc; a.v_ld = N; a.v_tail = 1; a.out_state = res; a.batch = C; a.cmask = cmask;
+            if ((rc_dense = dispatch<KS_OP_MATVEC>(cls, n, m, a, jws, jws_bytes, stream)) != 0) return rc_dense;
+            KS_LAUNCH(ksd::residual_kernel, 148, 256, 0, s, res, (const double*)rhs0, (size_t)C * nm);
+          } else {
+            KS_LAUNCH(ksd::gemv_kernel, C, ksd::kThreads, x_smem, s, (const double*)J, (const double*)dxc, (const double*)rhs0, res, nm, N, 1, 0);
+          }
           r = res;
         }
         KS_LAUNCH(ksd::tri_solve_kernel, C, ksd::kThreads, vec_smem, s, (const double*)Lf, (const double*)Li, r, yv, nm);
-        KS_LAUNCH(ksd::gemv_kernel, C, ksd::kThreads, vec_smem, s, (const double*)J, (const double*)yv, (const double*)nullptr, dxc, nm, N, 0,
-                  it > 0 ? 1 : 0);
+        if (mfree) {  // dx (+)= J^T y; the W area is free once the factorisation stands
+          double* dst = it > 0 ? J : dxc;
+          KsEvalArgs a;
+          std::memset(&a, 0, sizeof(a));
+          a.modes = Uc; a.params = Pc; a.vmodes = yv; a.out_state = dst; a.out_ld = N; a.out_tail = 1; a.batch = C; a.cmask = cmask;
+          if ((rc_dense = dispatch<KS_OP_RMATVEC>(cls, n, m, a, jws, jws_bytes, stream)) != 0) return rc_dense;
+          if (it > 0) KS_LAUNCH(ksd::add_kernel, 148, 256, 0, s, dxc, (const double*)dst, (size_t)C * N);
+        } else {
+          KS_LAUNCH(ksd::gemv_kernel, C, ksd::kThreads, vec_smem, s, (const double*)J, (const double*)yv, (const double*)nullptr, dxc, nm, N, 0,
+                    it > 0 ? 1 : 0);
+        }
       }
       KS_LAUNCH(ksd::scatter_kernel, C, 256, 0, s, idx, (const double*)dxc, xsol, N);
       n_steps += C;

@@ -54,9 +54,11 @@ struct KsEvalArgs {
   int out_tail;           // rmatvec/costgrad: write free parameter components to out_state[b*out_ld + Nm + slot]
   int pingpong;           // 32x32 variant 6: the two warp groups of a CTA take turns on the fp64 pipe (ks_debug_warp32_pingpong)
   int stagger_ns;         // 32x32 kernels: start delay between the warps of one scheduler (tuning, ks_debug_warp32_stagger)
-  int jac_ncol;           // 32x32 matvec, Jacobian mode (> 0): evaluation e is column e % jac_ncol of the Jacobian of orbit
-                          // e / jac_ncol -- u from modes / params [e / jac_ncol], v = the unit vector of that cdof slot
-                          // (made in the kernel), result at out_state + e * out_ld
+  // 32x32 matvec / rmatvec on the one-orbit-per-warp kernel, column modes of the dense Newton step:
+  int u_div;              // > 0: evaluation e works on orbit e / u_div (u from modes / params [e / u_div], read in place)
+  int unit_v;             // with u_div: v is the unit vector of cdof slot e % u_div, made in the kernel (nothing read)
+                          //   Jacobian:  matvec,  u_div = N,  unit_v = 1           -> column e % N of J at out_state + e * out_ld
+                          //   J J^T:     rmatvec, u_div = Nm, unit_v = 1 (w = J^T e_j), then matvec, u_div = Nm, v = w from memory
   // Operator cache of the Krylov drivers (64x64 CTA-resident kernel): during one inner solve u is fixed, so N(u, u) =
   // 1/2 Dx(u u) is computed once (by the eqn evaluation that opens the outer iteration, n_out) and reused by every matvec /
   // rmatvec of the solve (n_cache), which then skip the two forward transforms of u u.

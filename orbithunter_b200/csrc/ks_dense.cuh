@@ -49,6 +49,13 @@ __global__ void scatter_kernel(const int* idx, const double* dx, double* xsol, i
   const int c = blockIdx.x, b = idx[c];
   for (int i = threadIdx.x; i < N; i += blockDim.x) xsol[(size_t)b * N + i] = dx[(size_t)c * N + i];
 }
+// out += in  /  out = rhs - out  over n doubles (matrix-free refinement: the products come from the matvec / rmatvec kernels)
+__global__ void add_kernel(double* out, const double* in, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] += in[i];
+}
+__global__ void residual_kernel(double* out, const double* rhs, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = rhs[i] - out[i];
+}
 // G += lambda[c] * I
 __global__ void shift_diag_kernel(double* G, const double* lambda, int nm) {
   const int c = blockIdx.x;

@@ -122,8 +122,8 @@ int launch_warp32(int variant, const KsEvalArgs& a, cudaStream_t s) {
   }
   if constexpr (OP == KS_OP_MATVEC || OP == KS_OP_RMATVEC) {
     // variant 4 (default): matvec / rmatvec on the one-orbit-per-warp kernel too (variant 7 keeps them on the two-orbits-per-warp
-    // kernel); the Jacobian mode (jac_ncol > 0) exists only there
-    if (variant == 4 || a.jac_ncol > 0) return launch_warp32x1_pc<CLS, OP, false>(a, s);
+    // kernel); the column modes (u_div > 0) exist only there
+    if (variant == 4 || a.u_div > 0) return launch_warp32x1_pc<CLS, OP, false>(a, s);
   }
   return launch_warp32_as<CLS, OP>(a, s);
 }

@@ -163,9 +163,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
   constexpr double cN = 0.5 / (64.0 * 4096.0), cP = 1.0 / (64.0 * 4096.0);
   // column offset of this lane's half inside a modes row: full classes [Re_x | Im_x], half classes a single block
   const int coff = (FULL ? h * 15 : 0) + cc;
-  const int jac = VOP ? a.jac_ncol : 0;  // Jacobian mode: evaluation e = (orbit e / jac, column e % jac)
+  const int udiv = VOP ? a.u_div : 0;            // column modes: evaluation e works on orbit e / udiv ...
+  const bool unit_v = VOP && udiv > 0 && a.unit_v;  // ... with v = the unit vector of cdof slot e % udiv
   const int v_ld = a.v_ld ? a.v_ld : NM;
-  auto uidx = [&](int e) { return jac > 0 ? e / jac : e; };
+  auto uidx = [&](int e) { return udiv > 0 ? e / udiv : e; };
 
   // u's half tuples reach the registers through a cp.async landing zone filled one orbit ahead (the first-touch DRAM
   // latency of the modes was 26 % of the warp-issue samples with plain loads: profiles/r01g_*)
@@ -263,10 +264,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
     ksw32::cp_async_commit();
   };
   // matvec / rmatvec: v's half tuples land in the second lane-private area (same slots as u's); issued once phase C has read
-  // the current orbit's v.  Jacobian mode has no v in memory.
+  // the current orbit's v.  Unit-vector modes have no v in memory.
   [[maybe_unused]] auto prefetch_v = [&](int orb) {
     if constexpr (VOP) {
-      if (orb < a.batch && jac == 0) {
+      if (orb < a.batch && !unit_v) {
         const double* Vn = a.vmodes + (size_t)orb * v_ld + coff;
         static_for<0, 16>([&](auto Jc) {
           constexpr int J = decltype(Jc)::value;
@@ -433,8 +434,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
     [[maybe_unused]] int jrow = -1, jcol = -1;
     if constexpr (VOP) {
       int jpar = -1;
-      if (jac > 0) {
-        const int col = orbit % jac;
+      if (unit_v) {
+        const int col = orbit % udiv;
         if (col < NM) {
           jrow = col / COLS;
           jcol = col - jrow * COLS;
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int slot = ks::free_slot(a.cmask, i);
-          if (jac > 0) v3[i] = (slot >= 0 && slot == jpar) ? 1.0 : 0.0;
+          if (unit_v) v3[i] = (slot >= 0 && slot == jpar) ? 1.0 : 0.0;
           else v3[i] = a.v_tail ? (slot < 0 ? 0.0 : a.vmodes[(size_t)orbit * v_ld + NM + slot]) : a.vparams[orbit * 3 + i];
         }
         vt = fix_t ? 0.0 : v3[0] * (-1.0 / T);
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) ks_warp32x1_ker
     [[maybe_unused]] auto vhalf = [&](auto Jc, double& v1, double& v2) {
       constexpr int J = decltype(Jc)::value;
       const bool pres = (J & 1) ? presO : presE;
-      if (jac > 0) {
+      if (unit_v) {
         const bool mine = pres && colact && jcol == coff;
         v1 = (mine && jrow == J) ? 1.0 : 0.0;
         v2 = (J > 0 && mine && jrow == 15 + J) ? 1.0 : 0.0;

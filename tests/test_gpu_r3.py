@@ -342,10 +342,11 @@ def test_batched_jacobian_equals_matvec_on_unit_vectors(cid, shape):
 
 @pytest.mark.gpu
 def test_dense_newton_jacobian_mode_changes_no_result():
-    """hunt('lstsq') at 32x32 with the Jacobian built by the kernel's Jacobian mode (default) and by the batched matvec over a
-    stored identity.  The two Jacobians differ in the last bits (different summation order), and Newton far from an orbit
-    amplifies that, so: at least 85 % of the exit codes agree and the sets of converged seeds overlap by 80 % or more (the same
-    bar as the comparison with the reference, test_cfg0_status_table_matches_reference)."""
+    """hunt('lstsq') at 32x32 by the three routes of ks_newton_dense: matrix-free J J^T (2, the default: rmatvec over unit
+    vectors, matvec over the result, no Jacobian stored), Jacobian by the kernel's Jacobian mode + GEMM (1), Jacobian by a
+    batched matvec over a stored identity + GEMM (0).  Routes 1 and 0 produce the same bits; route 2 sums in another order,
+    and Newton far from an orbit amplifies that, so: at least 85 % of the exit codes agree and the sets of converged seeds
+    overlap by 80 % or more (the bar of the comparison with the reference, test_cfg0_status_table_matches_reference)."""
     from orbithunter_b200 import BatchedOrbitKS, _lib
     from orbithunter_b200.optimize import hunt
 
@@ -354,12 +355,13 @@ def test_dense_newton_jacobian_mode_changes_no_result():
     w = hunt(u, "adj", maxiter=10000).orbit
     res = {}
     try:
-        for on in (1, 0):
-            L.ks_debug_dense_jacobian_mode(on)
-            res[on] = hunt(w, "lstsq", maxiter=200, tol=1e-10)
+        for mode in (2, 1, 0):
+            L.ks_debug_dense_jacobian_mode(mode)
+            res[mode] = hunt(w, "lstsq", maxiter=200, tol=1e-10)
     finally:
-        L.ks_debug_dense_jacobian_mode(1)
-    a, b = res[1], res[0]
+        L.ks_debug_dense_jacobian_mode(2)
+    assert torch.equal(res[1].status, res[0].status) and torch.equal(res[1].orbit.state, res[0].orbit.state)
+    a, b = res[2], res[1]
     assert (a.status == b.status).float().mean().item() >= 0.85
     ca, cb = (a.status == 1).cpu().numpy(), (b.status == 1).cpu().numpy()
     assert ca.sum() > 0 and (ca & cb).sum() >= 0.8 * max(ca.sum(), cb.sum())

@@ -47,7 +47,7 @@ def main():
         L.ks_debug_warp32_variant(4)
     u = BatchedOrbitKS.from_seeds(np.arange(args.dense_batch), (44.0, 44.0, 0.0), "OrbitKS", (32, 32))
     w = hunt(u, "adj", maxiter=10000).orbit
-    for on in (1, 0, 1, 0):
+    for on in (2, 1, 0, 2, 1, 0):
         L.ks_debug_dense_jacobian_mode(on)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -56,7 +56,7 @@ def main():
         dt = time.perf_counter() - t0
         print(json.dumps({"dense_batch": args.dense_batch, "jacobian_mode": on, "dense_stage_s": dt,
                           "converged": int((r.status == 1).sum()), "dense_solves": int(r.dense_solves)}), flush=True)
-    L.ks_debug_dense_jacobian_mode(1)
+    L.ks_debug_dense_jacobian_mode(2)
     # Jacobian alone
     for on in (1,):
         t = timed(lambda: w.jacobian() if w.batch <= 256 else BatchedOrbitKS(w.state[:256].contiguous(), w.parameters[:256].contiguous(),
