@@ -79,7 +79,7 @@ SWEEP_FIELDS = RECORD_FIELDS + ("code",)
 
 
 def two_stage_sweep(n_seeds, refine, T=44.0, L=33.4, cls_name="OrbitKS", discretization=(32, 32), first_seed=0, adj_maxiter=10000,
-                    adj_tol=1e-6, dense_maxiter=200, dense_tol=1e-10, dense_chunk=256, device=None):
+                    adj_tol=1e-6, dense_maxiter=200, dense_tol=1e-10, dense_chunk=None, device=None):
     """BASELINE configs[4]: the orbit-hunting sweep, strong-scaled over the initialised process group.
 
     Every rank takes the contiguous shard of seeds [first_seed, first_seed + n_seeds) that ``shard_bounds`` gives it,
@@ -123,7 +123,8 @@ def two_stage_sweep(n_seeds, refine, T=44.0, L=33.4, cls_name="OrbitKS", discret
     tm["dense_solves"] = 0.0
     if n_ref > 0:
         sub = r1.orbit._like(r1.orbit.state[:n_ref].contiguous(), r1.orbit.parameters[:n_ref].contiguous())
-        r2 = hunt(sub, "lstsq", maxiter=dense_maxiter, tol=dense_tol, chunk=dense_chunk)
+        chunk_kw = {} if dense_chunk is None else {"chunk": dense_chunk}
+        r2 = hunt(sub, "lstsq", maxiter=dense_maxiter, tol=dense_tol, **chunk_kw)
         t = lap("dense_newton_s", t)
         codes, _ = r2.orbit.preprocess_codes()
         status[:n_ref] = r2.status.to(torch.float64)
