@@ -1,4 +1,8 @@
-// 32x32 eqn / costgrad, "one orbit per warp, state in registers" form (variant 4).
+// 32x32 eqn / costgrad / matvec / rmatvec and the fused adjoint-descent passes, "one orbit per warp, state in registers" form
+// (variant 4, the default for every 32x32 operation).  matvec / rmatvec also have COLUMN MODES for the dense Newton step
+// (KsEvalArgs::u_div, unit_v): evaluation e works on orbit e / u_div and, with unit_v, on the unit vector of cdof slot
+// e % u_div made in registers -- the Jacobian (matvec over unit vectors) and, the route ks_newton_dense takes, J J^T column by
+// column as J (J^T e_j) without a Jacobian in memory.
 //
 // Same mathematics and reference citations as ks_warp32.cuh, different work decomposition, chosen after profiling the
 // two-orbits-per-warp kernels (profiles/r01*): those need 128 registers of transform buffer per lane plus 31-47 KB of
