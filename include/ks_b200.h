@@ -192,13 +192,16 @@ int ks_newton_krylov(int cls, int n, int m, int batch, double* modes, double* pa
                      int32_t* nit_out, double* cost_out, long long* counters_out, int check_every, void* ws,
                      size_t ws_bytes, void* stream);
 
-/* hunt(..., 'lstsq'): _lstsq (optimize.py:855-1022, no preconditioning) for a whole batch.  Each outer step builds the
- * dense Jacobians of the orbits still in the loop (OrbitKS.jacobian, ks/orbits.py:557-657: one batched matvec over the
- * identity), takes dx = the minimum-norm solution of J dx = -F (the reference: scipy.linalg.lstsq) as J^T (J J^T)^-1 (-F) by
+/* hunt(..., 'lstsq'): _lstsq (optimize.py:855-1022, no preconditioning) for a whole batch.  Each outer step takes, for the
+ * orbits still in the loop, dx = the minimum-norm solution of J dx = -F (the reference: OrbitKS.jacobian, ks/orbits.py:557-657,
+ * then scipy.linalg.lstsq) as J^T (J J^T)^-1 (-F).  J J^T: at 32x32 column by column as J (J^T e_j) -- an rmatvec launch over
+ * unit vectors made in the kernel, then a matvec launch over the result, no Jacobian in memory; other sizes: the dense
+ * Jacobian (one batched matvec over the identity) and batched GEMMs.  Then
  * a blocked Cholesky factorisation with `refine` rounds of iterative refinement (breakdown -> Tikhonov shift), then the
  * same line search / _process_correction as ks_newton_krylov.  `chunk` orbits are factored at a time (workspace about
  * 3 x 8 x (Nm + 3)^2 bytes per orbit of the chunk); the batched fp64 GEMMs go through cuBLAS (loaded at run time).
- * counters_out: Jacobian columns evaluated, dense solves, line-search evaluations, outer iterations. */
+ * counters_out: operator applications per orbit spent on J J^T / the Jacobian, dense solves, line-search evaluations,
+ * outer iterations. */
 size_t ks_newton_dense_workspace_bytes(int cls, int n, int m, int batch, int chunk);
 int ks_newton_dense(int cls, int n, int m, int batch, double* modes, double* params, uint32_t cmask, double tol, double ftol,
                     int maxiter, double min_step, int chunk, int refine, int32_t* status_out, int32_t* nit_out,
