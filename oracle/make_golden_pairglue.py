@@ -60,6 +60,26 @@ def main():
                 out[f"{cid}/pair/{tag}{axis}_params"] = np.array(best.parameters, float)
                 out[f"{cid}/pair/{tag}{axis}_cost"] = np.array(best.cost())
                 print(cid, axis, tag, best.state.shape, best.parameters, float(best.cost()), flush=True)
+    # --- slicing and fundamental domains (core.py:553-668; ks/orbits.py:2770-2833, :3010-3014, :3229-3252, :3688-3711)
+    for cid, C in CLASSES.items():
+        a = C(state=out[f"{cid}/a"], basis="field", parameters=tuple(out[f"{cid}/a_params"]))
+        cut = a[2:10, 4:16]
+        out[f"{cid}/getitem"], out[f"{cid}/getitem_params"] = cut.state, np.array(cut.parameters, float)
+        row = a[3:4, :]
+        out[f"{cid}/getitem_row_params"] = np.array(row.parameters, float)
+        if cid == 0:
+            continue
+        for half in ((0,) if cid == 1 else (0, 1)):
+            kw = {} if cid == 1 else {"half": half}
+            fd = a.to_fundamental_domain(**kw)
+            out[f"{cid}/to_fd{half}"], out[f"{cid}/to_fd{half}_params"] = fd.state, np.array(fd.parameters, float)
+            back = fd.from_fundamental_domain(**kw)
+            out[f"{cid}/from_fd{half}"], out[f"{cid}/from_fd{half}_params"] = back.state, np.array(back.parameters, float)
+            fdm = a.transform(to="modes").to_fundamental_domain(**kw)
+            out[f"{cid}/to_fd{half}_modes"] = fdm.state
+        members = list(a.group_orbit(discrete=True, fundamental_domain=True))
+        out[f"{cid}/group/discrete_fd"] = np.stack([g.state for g in members])
+        out[f"{cid}/group/discrete_fd_params"] = np.array([g.parameters for g in members], float)
     np.savez_compressed(os.path.join(GOLD, "ks_pairglue.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -598,6 +598,22 @@ class OrbitKS:
         t, x, sft = self.parameters
         return f._new(state=-1.0 * np.roll(np.fliplr(f.state), 1, axis=axis), parameters=(t, x, -1 * sft)).transform(to=self.basis)
 
+    def __getitem__(self, key):
+        """Slice of the state with the dimensions scaled along (core.py:553-668): an axis cut to a fraction of its points
+        keeps that fraction of its period / length, an axis cut to one point gets dimension 0; only basic indexing that keeps
+        both axes is allowed."""
+        try:
+            cut = self.state[key]
+        except IndexError as ie:
+            raise ValueError("attempting to slice an Orbit whose state is empty." if self.size == 0 else "invalid slice") from ie
+        if cut.ndim != self.state.ndim:
+            raise ValueError(f"{type(self).__name__}.__getitem__ does not support arguments which squeeze, flatten, or otherwise "
+                             "reduce the dimension of the state array")
+        if self.parameters is None:
+            return self._new(state=cut, discretization=None)
+        dims = tuple(float(d) * (new / old) if new > 1 else 0.0 for d, new, old in zip(self.parameters[:2], cut.shape, self.shape))
+        return self._new(state=cut, parameters=dims + tuple(self.parameters[2:]), discretization=None)
+
     def to_fundamental_domain(self, **kwargs):
         return self  # core.py: no discrete symmetry, the whole tile
 
@@ -666,6 +682,31 @@ class RelativeOrbitKS(OrbitKS):
         assert self.frame == "comoving", "Mode truncation requires comoving frame; set padding=False if plotting"
         return super()._truncate(size, axis=axis)
 
+    def change_reference_frame(self, frame):
+        """Co-moving <-> physical frame (ks/orbits.py:2770-2833): every time row of the spatial modes is rotated by the phase
+        q_k * (+-S / T) * t, t running from T (first row) down to 0 (last row); S is always the shift from the co-moving to the
+        physical frame."""
+        if frame not in ("comoving", "physical"):
+            raise ValueError("Trying to change to unrecognizable reference frame.")
+        if frame == self.frame:
+            return self
+        shift = self.s if frame == "physical" else -1.0 * self.s
+        sm = self.transform(to="spatial_modes").state
+        k = int(self.m // 2) - 1
+        t = np.flipud(np.linspace(0, self.t, num=self.n, endpoint=True)).reshape(-1, 1)
+        q = (2 * np.pi / self.x) * np.arange(1, k + 1).reshape(1, -1)
+        theta = (shift / self.t) * t * q
+        c, sn = np.cos(theta), np.sin(theta)
+        re, im = sm[:, :k], sm[:, k:]
+        rotated = np.concatenate((c * re + sn * im, -sn * re + c * im), axis=1)
+        return self._new(state=rotated, basis="spatial_modes", frame=frame).transform(to=self.basis)
+
+    def to_fundamental_domain(self, **kwargs):
+        return self.change_reference_frame("physical")  # ks/orbits.py:3013-3014
+
+    def from_fundamental_domain(self, **kwargs):
+        return self.change_reference_frame("comoving")  # ks/orbits.py:3010-3011
+
     def populate(self, attr="all", **kwargs):
         # the reference resets S to 0 unless it estimates a shift from an existing state (ks/orbits.py:2872-2883);
         # shift estimation (calculate_spatial_shift, fsolve on the host) is outside the hot path.
@@ -687,16 +728,19 @@ class _HalfColumnMixin:
         return shape[0] + 1, 2 * shape[1] + 2
 
 
-def _no_fundamental_domain(self, *args, **kwargs):
-    raise NotImplementedError("fundamental-domain slicing (ks/orbits.py:3229-3252, :3688-3711, :3010-3014) is not provided")
-
-
-RelativeOrbitKS.to_fundamental_domain = RelativeOrbitKS.from_fundamental_domain = _no_fundamental_domain
-
-
 class ShiftReflectionOrbitKS(_HalfColumnMixin, OrbitKS):
     _cls_name = "ShiftReflectionOrbitKS"
-    to_fundamental_domain = from_fundamental_domain = _no_fundamental_domain
+
+    def to_fundamental_domain(self, half=0, **kwargs):
+        """One half of the period (ks/orbits.py:3688-3700): the last n/2 rows for half 0, the first n/2 otherwise."""
+        f, h = self.transform(to="field"), int(self.n // 2)
+        return (f[-h:, :] if half == 0 else f[:-h, :]).transform(to=self.basis)
+
+    def from_fundamental_domain(self, half=0, **kwargs):
+        """The full period from one half and its reflection (ks/orbits.py:3702-3711)."""
+        f = self.transform(to="field")
+        joined = f.reflection().concat(f, axis=0) if half == 0 else f.concat(f.reflection(), axis=0)
+        return joined.transform(to=self.basis)
 
     def concat(self, other, axis=0):
         """ks/orbits.py:3640-3676: joined in space, the result is rolled by half of the second tile's width."""
@@ -706,7 +750,17 @@ class ShiftReflectionOrbitKS(_HalfColumnMixin, OrbitKS):
 
 class AntisymmetricOrbitKS(_HalfColumnMixin, OrbitKS):
     _cls_name = "AntisymmetricOrbitKS"
-    to_fundamental_domain = from_fundamental_domain = _no_fundamental_domain
+
+    def to_fundamental_domain(self, half=0, **kwargs):
+        """One half of the domain (ks/orbits.py:3240-3252): the first m/2 columns for half 0, the last m/2 otherwise."""
+        f, h = self.transform(to="field"), int(self.m // 2)
+        return (f[:, :-h] if half == 0 else f[:, -h:]).transform(to=self.basis)
+
+    def from_fundamental_domain(self, half=0, **kwargs):
+        """The full domain from one half and its reflection (ks/orbits.py:3229-3238)."""
+        f = self.transform(to="field")
+        joined = f.concat(f.reflection(), axis=1) if half == 0 else f.reflection().concat(f, axis=1)
+        return joined.transform(to=self.basis)
 
     @staticmethod
     def _default_shape():

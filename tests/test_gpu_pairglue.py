@@ -105,3 +105,37 @@ def test_pairwise_boundary_cost_and_generator(gp):
                 dist.append(np.sqrt(np.sum((A[:, -1] - B[:, 0]) ** 2) + np.sum((A[:, 0] - B[:, -1]) ** 2)))
         ga, gb = pairs[int(np.argmin(dist))]
         assert relerr(best.state, ga.concat(gb, axis=axis).state) < 1e-13
+
+
+@pytest.mark.parametrize("cid", range(4))
+def test_slicing_and_fundamental_domains(gp, cid):
+    """Orbit.__getitem__ (core.py:553-668), RelativeOrbitKS.change_reference_frame (ks/orbits.py:2770-2833) and the
+    fundamental domains of the discrete-symmetry classes (:3229-3252, :3688-3711) against the reference's outputs, in the
+    field and in the modes basis, and group_orbit(discrete=True, fundamental_domain=True)."""
+    a, _ = _pair(gp, cid)
+    cut = a[2:10, 4:16]
+    assert np.array_equal(cut.state, gp[f"{cid}/getitem"]) and np.allclose(cut.parameters, gp[f"{cid}/getitem_params"], rtol=1e-14)
+    assert tuple(cut.discretization) == (8, 12)
+    assert np.allclose(a[3:4, :].parameters, gp[f"{cid}/getitem_row_params"])
+    with pytest.raises(ValueError):
+        a[3]
+    if cid == 0:
+        assert a.to_fundamental_domain() is a and a.from_fundamental_domain() is a
+        return
+    for half in ((0,) if cid == 1 else (0, 1)):
+        kw = {} if cid == 1 else {"half": half}
+        fd = a.to_fundamental_domain(**kw)
+        assert fd.state.shape == gp[f"{cid}/to_fd{half}"].shape
+        assert relerr(fd.state, gp[f"{cid}/to_fd{half}"]) < 1e-12 and np.allclose(fd.parameters, gp[f"{cid}/to_fd{half}_params"], rtol=1e-14)
+        back = fd.from_fundamental_domain(**kw)
+        assert relerr(back.state, gp[f"{cid}/from_fd{half}"]) < 1e-12
+        assert np.allclose(back.parameters, gp[f"{cid}/from_fd{half}_params"], rtol=1e-14)
+        fdm = a.transform(to="modes").to_fundamental_domain(**kw)
+        assert fdm.basis == "modes" and relerr(fdm.state, gp[f"{cid}/to_fd{half}_modes"]) < 1e-12
+    if cid == 1:
+        assert fd.frame == "physical" and back.frame == "comoving" and relerr(back.state, a.state) < 1e-12
+    members = list(a.group_orbit(discrete=True, fundamental_domain=True))
+    want, wp = gp[f"{cid}/group/discrete_fd"], gp[f"{cid}/group/discrete_fd_params"]
+    assert len(members) == len(want)
+    for g, w, p in zip(members, want, wp):
+        assert relerr(g.state, w) < 1e-12 and np.allclose(g.parameters, p)
