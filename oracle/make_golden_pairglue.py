@@ -80,6 +80,19 @@ def main():
         members = list(a.group_orbit(discrete=True, fundamental_domain=True))
         out[f"{cid}/group/discrete_fd"] = np.stack([g.state for g in members])
         out[f"{cid}/group/discrete_fd_params"] = np.array([g.parameters for g in members], float)
+    # --- the pairwise search over fundamental domains (gluing.py:424-496 with fundamental_domain=True)
+    for cid in (2, 3):
+        C = CLASSES[cid]
+        a = C(state=out[f"{cid}/a"], basis="field", parameters=tuple(out[f"{cid}/a_params"]))
+        b = C(state=out[f"{cid}/b"], basis="field", parameters=tuple(out[f"{cid}/b_params"]))
+        for axis in (0, 1):
+            for tag, kw in (("default", dict(rolls=(4, 4))), ("discrete", dict(discrete=True))):
+                best = expensive_pairwise_glue(np.array([a, b]).reshape((2, 1) if axis == 0 else (1, 2)), objective="cost", axis=axis,
+                                               fundamental_domain=True, **kw)
+                out[f"{cid}/pairfd/{tag}{axis}"] = best.state
+                out[f"{cid}/pairfd/{tag}{axis}_params"] = np.array(best.parameters, float)
+                out[f"{cid}/pairfd/{tag}{axis}_cost"] = np.array(best.cost())
+                print("fd", cid, axis, tag, best.state.shape, best.parameters, float(best.cost()), flush=True)
     np.savez_compressed(os.path.join(GOLD, "ks_pairglue.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -316,8 +316,6 @@ def pairwise_group_orbit(orbit_pair, **kwargs):
 def _group_fields(orbit, kwargs):
     """The fields of ``orbit.group_orbit(**kwargs)`` as one device tensor [G, n, m], in the generator's order, and the sign
     each member's spatial shift carries (reflections negate it; ks/orbits.py:1143-1170, :1355-1401)."""
-    if kwargs.get("fundamental_domain", False):
-        raise NotImplementedError("expensive_pairwise_glue(fundamental_domain=True) is not provided")
     field = orbit.transform(to="field")
     F = torch.as_tensor(np.ascontiguousarray(field.state, dtype=np.float64)).cuda()
     n, m = F.shape
@@ -354,17 +352,36 @@ def expensive_pairwise_glue(orbit_pair, objective="cost", axis=0, **kwargs):
     "boundary_cost" -- the L2 distance of the rows / columns that meet (both seams when the axis is periodic); the reference
     raises AttributeError for the latter (gluing.py:466 calls ``periodic_dimension``, which does not exist), the evident
     intent is implemented.  Ties go to the first combination in the reference's iteration order, as its strict ``<`` does.
-    Group-orbit kwargs: ``rolls``, ``continuous``, ``discrete`` (ks/orbits.py:1355-1401); ``return_type``."""
+    Group-orbit kwargs: ``rolls``, ``continuous``, ``discrete`` (ks/orbits.py:1355-1401); ``return_type``;
+    ``fundamental_domain`` for the ShiftReflection and Antisymmetric classes (OrbitKS: no effect, as in the reference)."""
     pair = np.asarray(orbit_pair, dtype=object).ravel()
     a, b = pair[0], pair[1]
     return_type = kwargs.get("return_type", type(a))
     chunk = int(kwargs.get("chunk", 8192))
     GA, sa = _group_fields(a, kwargs)
     GB, _ = _group_fields(b, kwargs)
+    # fundamental_domain=True (reference gluing.py:470-487 with ks/orbits.py:3229-3252, :3688-3711): the members are cut to their
+    # fundamental domains, joined, and the join is completed with its reflection before it is scored
+    fd = bool(kwargs.get("fundamental_domain", False))
+    cls_name = type(a)._cls_name
+    if fd and cls_name == "RelativeOrbitKS":
+        raise NotImplementedError("expensive_pairwise_glue(fundamental_domain=True) is not provided for RelativeOrbitKS "
+                                  "(its fundamental domain is the physical reference frame)")
+    fd = fd and cls_name in ("ShiftReflectionOrbitKS", "AntisymmetricOrbitKS")
+    if fd and objective == "boundary_cost":
+        raise NotImplementedError("objective='boundary_cost' with fundamental_domain=True is not provided")
+    fd_axis = 0 if cls_name == "ShiftReflectionOrbitKS" else 1
+    if fd:
+        if fd_axis == 0:
+            GA, GB = GA[:, -(GA.shape[1] // 2):, :], GB[:, -(GB.shape[1] // 2):, :]
+        else:
+            GA, GB = GA[:, :, :-(GA.shape[2] // 2)], GB[:, :, :-(GB.shape[2] // 2)]
     if GA.shape[2 - axis] != GB.shape[2 - axis]:
         raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
     ta, xa, s0 = (a.parameters + (0.0,) * 3)[:3]
     tb, xb = b.parameters[:2]
+    # dimensions of the join (glue_dimensions): summed along the axis, averaged across it; cutting to the fundamental domain
+    # halves the symmetric dimension of both tiles and the completion doubles it again, so the result is the same either way
     dims = tuple((2 if i == axis else 1) * 0.5 * (p + q) for i, (p, q) in enumerate(((ta, tb), (xa, xb))))
     periodic = a.periodic_dimensions()[axis]
     sr_roll = GB.shape[2] // 2 if (return_type._cls_name == "ShiftReflectionOrbitKS" and axis == 1) else 0
@@ -389,6 +406,9 @@ def expensive_pairwise_glue(orbit_pair, objective="cost", axis=0, **kwargs):
             glued = torch.cat((GA[ia], GB[ib]), dim=1 + axis)
             if sr_roll:
                 glued = torch.roll(glued, sr_roll, dims=2)
+            if fd:
+                mirror = -torch.roll(torch.flip(glued, dims=(-1,)), 1, dims=-1)
+                glued = torch.cat((mirror, glued), dim=1) if fd_axis == 0 else torch.cat((glued, mirror), dim=2)
             params = torch.stack((torch.full_like(sa[ia], dims[0]), torch.full_like(sa[ia], dims[1]), sa[ia] * s0), dim=1)
             cost = BatchedOrbitKS(glued, params, return_type._cls_name, "field").transform("modes").cost()
         cmin = float(cost.min())
@@ -397,7 +417,13 @@ def expensive_pairwise_glue(orbit_pair, objective="cost", axis=0, **kwargs):
     ia, ib = best_idx // nb_members, best_idx % nb_members
     fa = a.transform(to="field")
     fb = b.transform(to="field")
-    ga = fa._new(state=GA[ia].cpu().numpy(), parameters=(ta, xa, float(sa[ia]) * s0))
-    gb = fb._new(state=GB[ib].cpu().numpy())
-    joined = ga.concat(gb, axis=axis)
+    if fd:  # the winner once more through the single-orbit methods: cut, join, complete
+        full_a, full_b = _group_fields(a, kwargs)[0][ia].cpu().numpy(), _group_fields(b, kwargs)[0][ib].cpu().numpy()
+        ga = fa._new(state=full_a, parameters=(ta, xa, float(sa[ia]) * s0)).to_fundamental_domain()
+        gb = fb._new(state=full_b).to_fundamental_domain()
+        joined = ga.concat(gb, axis=axis).from_fundamental_domain()
+    else:
+        ga = fa._new(state=GA[ia].cpu().numpy(), parameters=(ta, xa, float(sa[ia]) * s0))
+        gb = fb._new(state=GB[ib].cpu().numpy())
+        joined = ga.concat(gb, axis=axis)
     return return_type(**vars(joined)).transform(to=a.basis)

@@ -139,3 +139,25 @@ def test_slicing_and_fundamental_domains(gp, cid):
     assert len(members) == len(want)
     for g, w, p in zip(members, want, wp):
         assert relerr(g.state, w) < 1e-12 and np.allclose(g.parameters, p)
+
+
+@pytest.mark.parametrize("cid", [2, 3])
+def test_pairwise_glue_over_fundamental_domains(gp, cid):
+    """expensive_pairwise_glue(fundamental_domain=True) for the discrete-symmetry classes: members cut to their fundamental
+    domains, joined, completed with the reflection, scored -- all combinations of a call in one device batch; winner's cost,
+    parameters and norm are the reference's (ties as in test_expensive_pairwise_glue_matches_reference)."""
+    from orbithunter_b200.gluing import expensive_pairwise_glue
+
+    a, b = _pair(gp, cid)
+    for axis in (0, 1):
+        for tag, kw in (("default", dict(rolls=(4, 4))), ("discrete", dict(discrete=True))):
+            arr = np.array([a, b], dtype=object).reshape((2, 1) if axis == 0 else (1, 2))
+            best = expensive_pairwise_glue(arr, objective="cost", axis=axis, fundamental_domain=True, **kw)
+            key = f"{cid}/pairfd/{tag}{axis}"
+            assert type(best) is type(a) and best.state.shape == gp[key].shape
+            assert best.cost() == pytest.approx(float(gp[key + "_cost"]), rel=1e-11), key
+            assert np.allclose(np.abs(best.parameters), np.abs(gp[key + "_params"]), rtol=1e-14), key
+            assert np.linalg.norm(best.state) == pytest.approx(np.linalg.norm(gp[key]), rel=1e-12), key
+    r = _pair(gp, 1)
+    with pytest.raises(NotImplementedError):
+        expensive_pairwise_glue(list(r), fundamental_domain=True, discrete=True)
